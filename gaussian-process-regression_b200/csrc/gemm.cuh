@@ -1,0 +1,482 @@
+// gemm.cuh -- the FP64 tensor-core (DMMA) GEMM core of libgprc and the tile policies built on it.
+//
+// One CTA (256 threads, 8 warps as 2 x 4) owns one 128 x 128 output tile; each warp owns 64 x 32 of it as
+// 8 x 4 m8n8k4 accumulator fragments (128 registers).  Operand k-slices (BK = 16) are staged in a 4-deep ring of
+// shared-memory buffers filled by the TMA engine with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) that complete
+// on per-stage mbarriers; rows are padded by 4 doubles so that every fragment load (LDS.64) is bank-conflict free.
+// FP64 DMMA runs at 64 FMA/clk/SM, i.e. one DMMA.8x8x4 per 16 clk per SM sub-partition, so the kernel is bound by
+// the tensor pipe: per k-slice a warp issues 12 LDS.64 for 32 DMMAs (19 % of the shared-memory bandwidth).
+//
+// Everything the library does at O(n^3) goes through this mainloop with a different policy:
+//   SyrkPolicy     C -= P P^T on lower tiles            Cholesky left-looking panel update and trailing update
+//   TrsmPolicy     C  = C Linv^T (in place)             Cholesky panel solve with the inverted diagonal block
+//   Trtri1Policy   T  = L21 W11 (stored transposed)     level-wise recursive inversion of L, first product
+//   Trtri2Policy   W21 = -W22 T                         ... second product
+//   TrmmNormPolicy colsum((W Ks)^2) per row block       predictive variance v = L^-1 K_star, R/GPRclass.R:162-164
+//   DgemmPolicy    C = beta C + alpha A op(B)           tests and the roofline microbenchmark
+#pragma once
+#include "common.cuh"
+
+namespace gprc {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
+constexpr int LDA_S = BM + 4;     // MN-major tile [BK][LDA_S]: (lane%4)*132 mod 16 = {0,4,8,12} -> conflict free
+constexpr int LDB_MN_S = BN + 4;  // MN-major B tile [BK][LDB_MN_S]
+constexpr int LDB_K_S = BK + 4;   // K-major B tile [BN][LDB_K_S]: (lane/4)*20 mod 16 = {0,4,8,12} per half warp
+constexpr int A_STAGE_DOUBLES = BK * LDA_S;
+constexpr int B_STAGE_DOUBLES = (BN * LDB_K_S > BK * LDB_MN_S) ? BN * LDB_K_S : BK * LDB_MN_S;
+constexpr int STAGE_DOUBLES = A_STAGE_DOUBLES + B_STAGE_DOUBLES;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 64;
+
+struct TileWork {
+  const double* A;  // element (m, k) at A[m + k * lda], m in [0, 128)
+  long lda;
+  const double* B;  // B_KMAJOR ? element (k, n) at B[k + n * ldb] : element (k, n) at B[n + k * ldb]
+  long ldb;
+  int k_begin, k_end;  // multiples of BK
+};
+
+using Acc = double[8][4][2];
+
+struct WarpCoord {
+  int lane, warp_m, warp_n;
+  __device__ __forceinline__ WarpCoord() {
+    lane = threadIdx.x & 31;
+    int w = threadIdx.x >> 5;
+    warp_m = w & 1;
+    warp_n = w >> 1;
+  }
+  // tile-local coordinates of accumulator element acc[mb][nb][r]
+  __device__ __forceinline__ int row(int mb) const { return warp_m * 64 + mb * 8 + (lane >> 2); }
+  __device__ __forceinline__ int col(int nb, int r) const { return warp_n * 32 + nb * 8 + 2 * (lane & 3) + r; }
+};
+
+template <bool B_KMAJOR>
+__device__ __forceinline__ void issue_stage(const TileWork& w, int k0, double* stage, uint32_t bar) {
+  const int tid = threadIdx.x;
+  uint32_t bytes = 0;
+  const void* src = nullptr;
+  uint32_t dst = 0;
+  if (tid < BK) {
+    src = w.A + (long)(k0 + tid) * w.lda;
+    dst = smem_u32(stage + tid * LDA_S);
+    bytes = BM * 8;
+  } else if (!B_KMAJOR) {
+    if (tid >= 32 && tid < 32 + BK) {
+      int r = tid - 32;
+      src = w.B + (long)(k0 + r) * w.ldb;
+      dst = smem_u32(stage + A_STAGE_DOUBLES + r * LDB_MN_S);
+      bytes = BN * 8;
+    }
+  } else {
+    if (tid >= 128) {
+      int r = tid - 128;
+      src = w.B + (long)r * w.ldb + k0;
+      dst = smem_u32(stage + A_STAGE_DOUBLES + r * LDB_K_S);
+      bytes = BK * 8;
+    }
+  }
+  mbar_arrive_expect_tx(bar, bytes);
+  if (bytes) bulk_g2s(dst, src, bytes, bar);
+}
+
+template <bool B_KMAJOR>
+__device__ __forceinline__ void compute_stage(const double* __restrict__ stage, const WarpCoord& wc, Acc& acc) {
+  const double* As = stage;
+  const double* Bs = stage + A_STAGE_DOUBLES;
+  const int lk = wc.lane & 3, lr = wc.lane >> 2;
+#pragma unroll
+  for (int ks = 0; ks < BK / 4; ++ks) {
+    double a[8], b[4];
+    const double* ap = As + (ks * 4 + lk) * LDA_S + wc.warp_m * 64 + lr;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) a[mb] = ap[mb * 8];
+    if (B_KMAJOR) {
+      const double* bp = Bs + (wc.warp_n * 32 + lr) * LDB_K_S + ks * 4 + lk;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) b[nb] = bp[nb * 8 * LDB_K_S];
+    } else {
+      const double* bp = Bs + (ks * 4 + lk) * LDB_MN_S + wc.warp_n * 32 + lr;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) b[nb] = bp[nb * 8];
+    }
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+  }
+}
+
+// acc += A(128 x K) * B(K x 128) over k in [k_begin, k_end)
+template <bool B_KMAJOR>
+__device__ __forceinline__ void gemm_mainloop(const TileWork& w, Acc& acc, double* smem, uint64_t* bars) {
+  const WarpCoord wc;
+  const int KT = (w.k_end - w.k_begin) / BK;
+  if (KT <= 0) return;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(bars + s), GEMM_THREADS);
+    mbar_fence_init();
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s)
+    if (s < KT) issue_stage<B_KMAJOR>(w, w.k_begin + s * BK, smem + s * STAGE_DOUBLES, smem_u32(bars + s));
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(smem_u32(bars + s), (kt / STAGES) & 1);
+    __syncthreads();  // every warp has finished reading the stage that is refilled below (consumed at kt - 1)
+    const int kn = kt + STAGES - 1;
+    if (kn < KT) {
+      const int sn = kn % STAGES;
+      issue_stage<B_KMAJOR>(w, w.k_begin + kn * BK, smem + sn * STAGE_DOUBLES, smem_u32(bars + sn));
+    }
+    compute_stage<B_KMAJOR>(smem + s * STAGE_DOUBLES, wc, acc);
+  }
+}
+
+template <class Policy>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const Policy p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_DOUBLES * 8);
+  TileWork w;
+  typename Policy::Tile t;
+  if (!p.setup(w, t)) return;  // depends on blockIdx only: uniform for the CTA
+  Acc acc;
+#pragma unroll
+  for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  p.prefetch(t);
+  gemm_mainloop<Policy::B_KMAJOR>(w, acc, smem, bars);
+  p.epilogue(t, acc, smem);
+}
+
+// decode a linear index into the lower triangle (i >= j) enumerated row by row: t = i (i + 1) / 2 + j
+__device__ __forceinline__ void tri_decode(long t, int& i, int& j) {
+  long ii = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (ii * (ii + 1) / 2 > t) --ii;
+  while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+  i = (int)ii;
+  j = (int)(t - ii * (ii + 1) / 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SYRK / panel update on lower tiles:  C(ti, tj) -= sum_{k in [k0, k1)} P(ti, k) P(tj, k)^T
+//   mode 0 (column): tj = col_tile, ti = col_tile + blockIdx.x
+//   mode 1 (trail):  (ti, tj) enumerate the lower triangle of tiles [first_tile, ntiles)
+// ---------------------------------------------------------------------------------------------------------------
+struct SyrkPolicy {
+  static constexpr bool B_KMAJOR = false;
+  double* A;
+  long ld;
+  int mode, first_tile, k0, k1;
+  struct Tile {
+    double* C;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    int ti, tj;
+    if (mode == 0) {
+      tj = first_tile;
+      ti = first_tile + blockIdx.x;
+    } else {
+      tri_decode(blockIdx.x, ti, tj);
+      ti += first_tile;
+      tj += first_tile;
+    }
+    w.A = A + (long)ti * NB;
+    w.lda = ld;
+    w.B = A + (long)tj * NB;
+    w.ldb = ld;
+    w.k_begin = k0;
+    w.k_end = k1;
+    t.C = A + (long)ti * NB + (long)tj * NB * ld;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile& t) const {
+    // pull the C tile (128 columns x 8 lines of 128 B) into L2 while the mainloop runs: 4 lines per thread
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int line = threadIdx.x + q * GEMM_THREADS;
+      prefetch_l2(t.C + (long)(line >> 3) * ld + (line & 7) * 16);
+    }
+  }
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      double* cp0 = t.C + (long)wc.col(nb, 0) * ld;
+      double* cp1 = cp0 + ld;
+      double c0[8], c1[8];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) {
+        c0[mb] = cp0[wc.row(mb)];
+        c1[mb] = cp1[wc.row(mb)];
+      }
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) {
+        cp0[wc.row(mb)] = c0[mb] - acc[mb][nb][0];
+        cp1[wc.row(mb)] = c1[mb] - acc[mb][nb][1];
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Panel solve with the inverted diagonal block:  A(ti, j) = A(ti, j) * Linv_j^T, ti = j + 1 + blockIdx.x, in place
+// (all k-slices of the tile are in shared memory / registers before the epilogue writes it back)
+// ---------------------------------------------------------------------------------------------------------------
+struct TrsmPolicy {
+  static constexpr bool B_KMAJOR = false;
+  double* A;
+  long ld;
+  const double* linv;  // 128 x 128 col-major: element (k, n) of the B operand is Linv[n, k] = linv[n + k * 128]
+  int j;
+  struct Tile {
+    double* C;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    int ti = j + 1 + blockIdx.x;
+    t.C = A + (long)ti * NB + (long)j * NB * ld;
+    w.A = t.C;
+    w.lda = ld;
+    w.B = linv;
+    w.ldb = NB;
+    w.k_begin = 0;
+    w.k_end = NB;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double* cp = t.C + (long)wc.col(nb, r) * ld;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) cp[wc.row(mb)] = acc[mb][nb][r];
+      }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Level-wise recursive inversion W = L^-1.  At a level with left-part size s (in tiles), group g covers tiles
+// [2 s g, 2 s g + s) (left, W11 known) and [2 s g + s, min(2 s g + 2 s, nt)) (right, W22 known):
+//   phase 1:  T   = L21 * W11      (k >= column tile: W11 is lower triangular)   stored TRANSPOSED in S
+//   phase 2:  W21 = - W22 * T      (k <= row tile: W22 is lower triangular)
+// grid = (s, s, groups): blockIdx.x = column tile tj, blockIdx.y = row tile ti (within the right part)
+// ---------------------------------------------------------------------------------------------------------------
+struct Trtri1Policy {
+  static constexpr bool B_KMAJOR = true;
+  const double* L;
+  const double* W;
+  double* S;
+  long ld;
+  int s, nt;
+  struct Tile {
+    double* C;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    const int g = blockIdx.z, tj = blockIdx.x, ti = blockIdx.y;
+    const int gl = 2 * s * g, gr = gl + s;
+    const int r = min(s, nt - gr);
+    if (ti >= r) return false;
+    w.A = L + (long)(gr + ti) * NB + (long)gl * NB * ld;
+    w.lda = ld;
+    w.B = W + (long)gl * NB + (long)(gl + tj) * NB * ld;
+    w.ldb = ld;
+    w.k_begin = tj * NB;
+    w.k_end = s * NB;
+    t.C = S + (long)(gl + tj) * NB + (long)(gr + ti) * NB * ld;  // transposed position
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+      double* cp = t.C + (long)wc.row(mb) * ld;  // row of T -> column of S
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        double2 v = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = v;
+      }
+    }
+  }
+};
+
+struct Trtri2Policy {
+  static constexpr bool B_KMAJOR = false;
+  double* W;
+  const double* S;
+  long ld;
+  int s, nt;
+  struct Tile {
+    double* C;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    const int g = blockIdx.z, tj = blockIdx.x, ti = blockIdx.y;
+    const int gl = 2 * s * g, gr = gl + s;
+    const int r = min(s, nt - gr);
+    if (ti >= r) return false;
+    w.A = W + (long)(gr + ti) * NB + (long)gr * NB * ld;
+    w.lda = ld;
+    w.B = S + (long)(gl + tj) * NB + (long)gr * NB * ld;  // element (k, n) = T[k, n] = S[n + k * ld]
+    w.ldb = ld;
+    w.k_begin = 0;
+    w.k_end = (ti + 1) * NB;
+    t.C = W + (long)(gr + ti) * NB + (long)(gl + tj) * NB * ld;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double* cp = t.C + (long)wc.col(nb, r) * ld;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) cp[wc.row(mb)] = -acc[mb][nb][r];
+      }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Predictive variance:  V = W * Ks  (W = L^-1 lower triangular n x n, Ks n x mc col-major), never stored: the
+// epilogue reduces the squares of each tile column and writes partial[ti][column]  (R/GPRclass.R:162-164:
+// v <- solve(L, K_star); colSums(v * v)).  Tiles are issued heaviest first (largest row tile = longest k range)
+// in groups of GROUP row tiles so that one wave of CTAs shares both W row panels and Ks column panels in L2.
+// If VoutT != nullptr the tile of V is stored as well, transposed (full predictive covariance, R/GPRclass.R:167).
+// ---------------------------------------------------------------------------------------------------------------
+struct TrmmNormPolicy {
+  static constexpr bool B_KMAJOR = true;
+  static constexpr int GROUP = 8;
+  const double* W;
+  long ldw;
+  const double* Ks;
+  long ldk;
+  double* partial;  // [nt][ldp]
+  long ldp;
+  double* VoutT;
+  long ldv;
+  int nt, ntc;  // row tiles of W, column tiles of Ks
+  struct Tile {
+    int ti, tc;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    const long b = blockIdx.x;
+    const long per_group = (long)GROUP * ntc;
+    const int g = (int)(b / per_group);
+    const long r = b % per_group;
+    const int hi = nt - 1 - g * GROUP;  // heaviest row tile of this group
+    const int gsize = min(GROUP, hi + 1);
+    const int tc = (int)(r / GROUP), ii = (int)(r % GROUP);
+    if (ii >= gsize) return false;
+    t.ti = hi - ii;
+    t.tc = tc;
+    w.A = W + (long)t.ti * NB;
+    w.lda = ldw;
+    w.B = Ks + (long)tc * NB * ldk;
+    w.ldb = ldk;
+    w.k_begin = 0;
+    w.k_end = (t.ti + 1) * NB;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double* smem) const {
+    const WarpCoord wc;
+    if (VoutT) {  // V^T[t + k * ldv]: test point t contiguous, so that Sigma = K** - V^T V is an "A B^T" product
+      double* vp = VoutT + (long)t.tc * NB + (long)t.ti * NB * ldv;
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) {
+        double* cp = vp + (long)wc.row(mb) * ldv;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+      }
+    }
+    __syncthreads();  // all stages consumed; shared memory is reused for the cross-warp reduction
+    double* red = smem;  // [2][128]
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) s = fma(acc[mb][nb][r], acc[mb][nb][r], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if ((wc.lane >> 2) == 0) red[wc.warp_m * 128 + wc.col(nb, r)] = s;
+      }
+    __syncthreads();
+    if (threadIdx.x < 128)
+      partial[(long)t.ti * ldp + (long)t.tc * NB + threadIdx.x] = red[threadIdx.x] + red[128 + threadIdx.x];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plain DGEMM (tests, roofline microbenchmark):  C = beta C + alpha A op(B)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool KMAJOR>
+struct DgemmPolicy {
+  static constexpr bool B_KMAJOR = KMAJOR;
+  const double* A;
+  long lda;
+  const double* B;
+  long ldb;
+  double* C;
+  long ldc;
+  double alpha, beta;
+  int K, tiles_m;
+  struct Tile {
+    double* C;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    // column-of-tiles major: consecutive CTAs share the B panel
+    const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+    w.A = A + (long)tm * NB;
+    w.lda = lda;
+    w.B = KMAJOR ? B + (long)tn * NB * ldb : B + (long)tn * NB;
+    w.ldb = ldb;
+    w.k_begin = 0;
+    w.k_end = K;
+    t.C = C + (long)tm * NB + (long)tn * NB * ldc;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double* cp = t.C + (long)wc.col(nb, r) * ldc;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) {
+          double v = alpha * acc[mb][nb][r];
+          if (beta != 0.0) v += beta * cp[wc.row(mb)];
+          cp[wc.row(mb)] = v;
+        }
+      }
+  }
+};
+
+template <class Policy>
+inline int launch_gemm(gprc_ctx* ctx, const Policy& p, dim3 grid) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    GPRC_CUDA(cudaFuncSetAttribute(gemm_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  gemm_kernel<Policy><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(p);
+  ctx->launches++;
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gprc

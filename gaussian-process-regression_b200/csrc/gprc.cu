@@ -1,0 +1,1332 @@
+// gprc.cu -- C ABI of libgprc (include/gprc.h): handles, host<->device plumbing and the launch sequences of the
+// GP hot path.  No Torch, no cuBLAS/cuSOLVER, no CPU fallback: every numerical step is one of the kernels in
+// cov.cuh / gemm.cuh / potrf.cuh / trsv.cuh / gpc.cuh.
+#include <climits>
+#include <algorithm>
+
+#include "cov.cuh"
+#include "gemm.cuh"
+#include "potrf.cuh"
+#include "trsv.cuh"
+#include "gpc.cuh"
+
+namespace gprc {
+thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur;
+    cudaGetDevice(&cur);
+    if (cur != prev && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class T>
+static int dmalloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return 0;
+}
+static void dfree(void* p) {
+  if (p) cudaFree(p);
+}
+
+// kernel spec: host struct -> device struct (sigma_vec uploaded, owned by the caller of make_spec)
+struct SpecHolder {
+  KSpecDev dev{};
+  double* d_sigma = nullptr;
+  ~SpecHolder() { dfree(d_sigma); }
+};
+static int make_spec(gprc_ctx* ctx, const gprc_kernel* k, int d, SpecHolder& h) {
+  GPRC_ARG(k != nullptr);
+  GPRC_ARG(k->id >= GPRC_CONSTANT && k->id <= GPRC_RATQUAD);
+  h.dev.id = k->id;
+  h.dev.c = k->c;
+  h.dev.sigma = k->sigma;
+  h.dev.p = k->p;
+  h.dev.l = k->l;
+  h.dev.gamma = k->gamma;
+  h.dev.alpha = k->alpha;
+  h.dev.sigma_vec = nullptr;
+  h.dev.sigma_len = 0;
+  if (k->id == GPRC_LINEAR && k->sigma_vec && k->sigma_len > 0) {
+    GPRC_ARG(k->sigma_len == 1 || k->sigma_len == d);  // stopifnot(length(sigma) == nrow(X)), R/GPRclass.R:298
+    GPRC_CHECK(dmalloc(&h.d_sigma, (size_t)k->sigma_len));
+    GPRC_CUDA(cudaMemcpyAsync(h.d_sigma, k->sigma_vec, k->sigma_len * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    h.dev.sigma_vec = h.d_sigma;
+    h.dev.sigma_len = k->sigma_len;
+  }
+  return 0;
+}
+
+__global__ void fill_kernel(double* p, long n, double v) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// dst (ldd) <- src (lds) for an r x c block, rest of the rp x cp padded block: 0, or 1 on the diagonal
+__global__ void pad_copy_kernel(const double* __restrict__ src, long lds, long r, long c, double* __restrict__ dst,
+                                long ldd, long rp, long cp, int pad_identity, double diag_add) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long j = blockIdx.y;
+  if (i >= rp || j >= cp) return;
+  double v;
+  if (i < r && j < c) {
+    v = src[i + j * lds];
+    if (i == j) v += diag_add;
+  } else {
+    v = (pad_identity && i == j) ? 1.0 : 0.0;
+  }
+  dst[i + j * ldd] = v;
+}
+// tmp[i + jj n] = (i >= j0 + jj) ? M[i + (j0 + jj) ld] : 0   (download of a lower-triangular factor, explicit zeros)
+__global__ void tril_slab_kernel(const double* __restrict__ M, long ld, long n, long j0, long nc,
+                                 double* __restrict__ tmp) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long jj = blockIdx.y;
+  if (i >= n || jj >= nc) return;
+  tmp[i + jj * n] = (i >= j0 + jj) ? M[i + (j0 + jj) * ld] : 0.0;
+}
+// columns [j0, j0 + nc) of a padded square matrix from a host-uploaded slab src (n x ncv, ld = n):
+// dst[i + j ld] = src + diag_add on the diagonal inside n x n; identity (or zero) in the padding
+__global__ void place_slab_kernel(const double* __restrict__ src, long n, long j0, long ncv, double* __restrict__ dst,
+                                  long ld, long n_pad, long nc, double diag_add, int pad_identity) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long jj = blockIdx.y;
+  if (i >= n_pad || jj >= nc) return;
+  const long j = j0 + jj;
+  double v;
+  if (i < n && jj < ncv) {
+    v = src[i + jj * n];
+    if (i == j) v += diag_add;
+  } else {
+    v = (pad_identity && i == j) ? 1.0 : 0.0;
+  }
+  dst[i + j * ld] = v;
+}
+__global__ void scale_rows_kernel(double* __restrict__ M, long ld, long rows, long cols, const double* __restrict__ s) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long j = blockIdx.y;
+  if (i < rows && j < cols) M[i + j * ld] *= s[i];
+}
+// y[col] = sum_i M[i, col] v[i] for a rows x cols column-major matrix
+__global__ void __launch_bounds__(256) gemv_t_rect_kernel(const double* __restrict__ M, long ld, long rows, long cols,
+                                                          const double* __restrict__ v, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= cols) return;
+  const double* Mp = M + col * ld;
+  double s = 0.0;
+  for (long i = lane; i < rows; i += 32) s = fma(Mp[i], v[i], s);
+  s = warp_sum(s);
+  if (lane == 0) y[col] = s;
+}
+
+static inline dim3 grid2(long rows, long cols) { return dim3((unsigned)((rows + 255) / 256), (unsigned)cols); }
+
+}  // namespace gprc
+
+using namespace gprc;
+
+// =================================================================================================================
+// handles
+// =================================================================================================================
+struct PredictWorkspace {
+  long mc = 0;          // chunk capacity (multiple of 128)
+  double* Ks = nullptr;     // n_pad x mc
+  double* pmean = nullptr;  // (n_pad / 64) x mc
+  double* pvar = nullptr;   // (n_pad / 128) x mc
+  double* kss = nullptr;    // mc
+  void release() {
+    dfree(Ks);
+    dfree(pmean);
+    dfree(pvar);
+    dfree(kss);
+    Ks = pmean = pvar = kss = nullptr;
+    mc = 0;
+  }
+};
+
+struct FactorState {  // a factored SPD matrix and everything derived from it
+  long n = 0, n_pad = 0;
+  double* L = nullptr;     // n_pad x n_pad, lower
+  double* dinv = nullptr;  // nt x 128 x 128 inverted diagonal blocks
+  double* diag = nullptr;  // n_pad
+  double* W = nullptr;     // lazy: L^-1, n_pad x n_pad lower
+  void release() {
+    dfree(L);
+    dfree(dinv);
+    dfree(diag);
+    dfree(W);
+    L = dinv = diag = W = nullptr;
+  }
+};
+
+struct gprc_gpr {
+  gprc_ctx* ctx = nullptr;
+  int d = 0;
+  bool precomputed = false;
+  gprc_kernel khost{};
+  SpecHolder spec;
+  double* X = nullptr;  // d x n
+  double* y = nullptr;  // n_pad
+  double* alpha = nullptr;
+  FactorState F;
+  PredictWorkspace ws;
+  double noise = 0, logp = 0;
+};
+
+struct gprc_gpc {
+  gprc_ctx* ctx = nullptr;
+  int d = 0;
+  bool precomputed = false;
+  SpecHolder spec;
+  double* X = nullptr;
+  double* y = nullptr;      // n_pad
+  double* K = nullptr;      // n_pad x n_pad full symmetric (freed after fit unless needed)
+  double* f = nullptr;      // n_pad  (f_hat)
+  double* sw = nullptr;     // n_pad  sqrt(W) at f_hat
+  double* gradl = nullptr;  // n_pad  (y + 1)/2 - P at f_hat
+  FactorState F;            // factor of B = I + W^1/2 K W^1/2
+  PredictWorkspace ws;
+};
+
+// =================================================================================================================
+// context
+// =================================================================================================================
+extern "C" int gprc_version(void) { return 100; }
+extern "C" const char* gprc_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
+  GPRC_ARG(out != nullptr);
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(-3, __FILE__, __LINE__, "no CUDA device: libgprc has no CPU fallback");
+  GPRC_ARG(device >= 0 && device < count);
+  GPRC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GPRC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 9) return set_error(-3, __FILE__, __LINE__, "libgprc is built for sm_100a (B200)");
+  gprc_ctx* c = new gprc_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  GPRC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
+  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
+  GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
+  GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_info), sizeof(long)));
+  *out = c;
+  return 0;
+}
+
+extern "C" void gprc_ctx_free(gprc_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : c->pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  cudaFree(c->d_info);
+  cudaFree(c->d_scalars);
+  cudaFreeHost(c->h_scalars);
+  cudaFreeHost(c->h_info);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
+  GPRC_ARG(c != nullptr);
+  if (option == GPRC_OPT_GRAM_DMMA) {
+    c->opt_gram_dmma = value;
+    return 0;
+  }
+  return set_error(-1, __FILE__, __LINE__, "unknown option");
+}
+
+extern "C" int gprc_ctx_sync(gprc_ctx* c) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static void resolve_timers(gprc_ctx* c) {
+  for (auto& p : c->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->timers[p.phase] += ms;
+    c->event_pool.push_back(p.a);
+    c->event_pool.push_back(p.b);
+  }
+  c->pending.clear();
+}
+
+extern "C" void gprc_ctx_reset_timers(gprc_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  resolve_timers(c);
+  for (int i = 0; i < GPRC_T_COUNT; ++i) c->timers[i] = 0.0;
+  c->launches = 0;
+}
+
+extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  resolve_timers(c);
+  if (ms)
+    for (int i = 0; i < GPRC_T_COUNT; ++i) ms[i] = c->timers[i];
+  if (launches) *launches = c->launches;
+  return 0;
+}
+
+// ---- device memory helpers --------------------------------------------------------------------------------------
+extern "C" int gprc_dev_malloc(gprc_ctx* c, void** dptr, unsigned long long bytes) {
+  GPRC_ARG(c != nullptr && dptr != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+  return 0;
+}
+extern "C" int gprc_dev_free(gprc_ctx* c, void* dptr) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  GPRC_CUDA(cudaFree(dptr));
+  return 0;
+}
+extern "C" int gprc_dev_h2d(gprc_ctx* c, void* dptr, const void* host, unsigned long long bytes) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int gprc_dev_d2h(gprc_ctx* c, void* host, const void* dptr, unsigned long long bytes) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int gprc_host_register(void* host, unsigned long long bytes) {
+  GPRC_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int gprc_host_unregister(void* host) {
+  GPRC_CUDA(cudaHostUnregister(host));
+  return 0;
+}
+
+// =================================================================================================================
+// (1) kernel-matrix build
+// =================================================================================================================
+static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d, long nA, const double* dB, long nB,
+                         double* out, long ldo, long rows_pad, long cols_pad, bool lower_only, bool symmetric,
+                         double diag_add, bool pad_identity, const double* rowscale, const double* weights,
+                         double* pmean, long ldpm) {
+  CovParams p;
+  p.k = k;
+  p.A = dA;
+  p.B = dB;
+  p.d = d;
+  p.nA = nA;
+  p.nB = nB;
+  p.out = out;
+  p.ldo = ldo;
+  p.rows_pad = rows_pad;
+  p.cols_pad = cols_pad;
+  p.lower_only = lower_only;
+  p.symmetric = symmetric;
+  p.diag_add = diag_add;
+  p.pad_identity = pad_identity;
+  p.rowscale = rowscale;
+  p.weights = weights;
+  p.pmean = pmean;
+  p.ldpm = ldpm;
+  return launch_cov(c, p);
+}
+
+extern "C" int gprc_cov_matrix(gprc_ctx* c, const gprc_kernel* k, const double* A, int d, long nA, const double* B,
+                               long nB, double* out) {
+  GPRC_ARG(c && k && A && B && out && d > 0 && nA >= 0 && nB >= 0);
+  if (nA == 0 || nB == 0) return 0;
+  DeviceGuard g(c->device);
+  SpecHolder spec;
+  GPRC_CHECK(make_spec(c, k, d, spec));
+  double *dA = nullptr, *dB = nullptr, *dout = nullptr;
+  const long rp = round_up(nA, CT);
+  // column chunks bound the device buffer (<= 2 GiB) and the grid's y extent
+  long cchunk = std::max<long>(CT, std::min<long>(round_up(nB, CT), ((2L << 30) / 8 / rp) / CT * CT));
+  cchunk = std::min<long>(cchunk, 65535L * CT);
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dA, (size_t)d * nA))) break;
+    if ((rc = dmalloc(&dB, (size_t)d * nB))) break;
+    if ((rc = dmalloc(&dout, (size_t)rp * cchunk))) break;
+    cudaMemcpyAsync(dA, A, sizeof(double) * d * nA, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dB, B, sizeof(double) * d * nB, cudaMemcpyHostToDevice, c->stream);
+    for (long c0 = 0; c0 < nB && rc == 0; c0 += cchunk) {
+      const long nc = std::min(cchunk, nB - c0);
+      {
+        PhaseTimer t(c, GPRC_T_BUILD_K);
+        rc = cov_build_dev(c, spec.dev, dA, d, nA, dB + c0 * d, nc, dout, rp, rp, round_up(nc, CT), false, false, 0.0,
+                           false, nullptr, nullptr, nullptr, 0);
+      }
+      if (rc) break;
+      cudaError_t e = cudaMemcpy2DAsync(out + c0 * nA, nA * sizeof(double), dout, rp * sizeof(double),
+                                        nA * sizeof(double), nc, cudaMemcpyDeviceToHost, c->stream);
+      if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == 0 && e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dA);
+  dfree(dB);
+  dfree(dout);
+  return rc;
+}
+
+extern "C" int gprc_cov_pointwise(gprc_ctx* c, const gprc_kernel* k, const double* A, const double* B, int d, long n,
+                                  double* out) {
+  GPRC_ARG(c && k && A && B && out && d > 0 && n >= 0);
+  if (n == 0) return 0;
+  DeviceGuard g(c->device);
+  SpecHolder spec;
+  GPRC_CHECK(make_spec(c, k, d, spec));
+  double *dA = nullptr, *dB = nullptr, *dout = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dA, (size_t)d * n))) break;
+    if ((rc = dmalloc(&dB, (size_t)d * n))) break;
+    if ((rc = dmalloc(&dout, (size_t)n))) break;
+    cudaMemcpyAsync(dA, A, sizeof(double) * d * n, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dB, B, sizeof(double) * d * n, cudaMemcpyHostToDevice, c->stream);
+    cov_pointwise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(spec.dev, dA, dB, d, n, dout);
+    c->launches++;
+    cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dA);
+  dfree(dB);
+  dfree(dout);
+  return rc;
+}
+
+// =================================================================================================================
+// factor + solve shared by GPR, logml and GPC
+// =================================================================================================================
+static int factor_alloc(FactorState& F, long n) {
+  F.n = n;
+  F.n_pad = round_up(std::max<long>(n, 1), NB);
+  GPRC_CHECK(dmalloc(&F.L, (size_t)F.n_pad * F.n_pad));
+  GPRC_CHECK(dmalloc(&F.dinv, (size_t)F.n_pad * NB));
+  GPRC_CHECK(dmalloc(&F.diag, (size_t)F.n_pad));
+  return 0;
+}
+
+// factor F.L in place; returns info through *info (0 ok).  Synchronises the stream.
+static int factor_run(gprc_ctx* c, FactorState& F, long* info) {
+  *c->h_info = LONG_MAX;
+  GPRC_CUDA(cudaMemcpyAsync(c->d_info, c->h_info, sizeof(long), cudaMemcpyHostToDevice, c->stream));
+  {
+    PhaseTimer t(c, GPRC_T_CHOL);
+    GPRC_CHECK(potrf_blocked(c, F.L, F.n_pad, F.n_pad, F.dinv, c->d_info, F.diag));
+  }
+  GPRC_CUDA(cudaMemcpyAsync(c->h_info, c->d_info, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  const long v = *c->h_info;
+  *info = (v == LONG_MAX) ? 0 : v;
+  return 0;
+}
+
+static int ensure_inverse(gprc_ctx* c, FactorState& F) {
+  if (F.W) return 0;
+  GPRC_CHECK(dmalloc(&F.W, (size_t)F.n_pad * F.n_pad));
+  PhaseTimer t(c, GPRC_T_TRTRI);
+  GPRC_CUDA(cudaMemsetAsync(F.W, 0, sizeof(double) * F.n_pad * F.n_pad, c->stream));  // zeros above the diagonal
+  // scratch for the level products aliases the (unused) strictly upper block triangle of the L buffer
+  GPRC_CHECK(trtri_levels(c, F.L, F.n_pad, F.n_pad, F.dinv, F.W, F.L));
+  return 0;
+}
+
+static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m) {
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  long want = round_up(std::max<long>(m, 1), NB);
+  // per test point: Ks column + partial rows
+  const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1);
+  const double budget = std::min(8.0e9, 0.45 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
+  long cap = (long)(budget / per_col) / NB * NB;
+  cap = std::max<long>(cap, NB);
+  cap = std::min<long>(cap, 1L << 20);
+  want = std::min(want, cap);
+  if (ws.mc >= want) return 0;
+  ws.release();
+  GPRC_CHECK(dmalloc(&ws.Ks, (size_t)n_pad * want));
+  GPRC_CHECK(dmalloc(&ws.pmean, (size_t)(n_pad / CT) * want));
+  GPRC_CHECK(dmalloc(&ws.pvar, (size_t)(n_pad / NB) * want));
+  GPRC_CHECK(dmalloc(&ws.kss, (size_t)want));
+  ws.mc = want;
+  return 0;
+}
+
+// variance pass on a chunk whose (row-scaled) K_star is already in ws.Ks:  pvar partials of colSums((W Ks)^2)
+static int variance_pass(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur_pad, double* VoutT, long ldv) {
+  const int nt = (int)(F.n_pad / NB), ntc = (int)(mcur_pad / NB);
+  TrmmNormPolicy p;
+  p.W = F.W;
+  p.ldw = F.n_pad;
+  p.Ks = ws.Ks;
+  p.ldk = F.n_pad;
+  p.partial = ws.pvar;
+  p.ldp = ws.mc;
+  p.VoutT = VoutT;
+  p.ldv = ldv;
+  p.nt = nt;
+  p.ntc = ntc;
+  const long groups = (nt + TrmmNormPolicy::GROUP - 1) / TrmmNormPolicy::GROUP;
+  PhaseTimer t(c, GPRC_T_VAR);
+  return launch_gemm(c, p, dim3((unsigned)(groups * TrmmNormPolicy::GROUP * ntc)));
+}
+
+// mean/var for m test points (device pointers).  weights: alpha (GPR) or (y+1)/2 - P (GPC); rowscale: sqrt(W) or null.
+static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F,
+                                 PredictWorkspace& ws, const double* weights, const double* rowscale,
+                                 const double* dXs, long m, double* dmean, double* dvar) {
+  GPRC_CHECK(ensure_inverse(c, F));
+  GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
+  for (long c0 = 0; c0 < m; c0 += ws.mc) {
+    const long mcur = std::min(ws.mc, m - c0);
+    const long mpad = round_up(mcur, NB);
+    {
+      PhaseTimer t(c, GPRC_T_BUILD_KS);
+      GPRC_CHECK(cov_build_dev(c, k, dX, d, F.n, dXs + c0 * d, mcur, ws.Ks, F.n_pad, F.n_pad, mpad, false, false, 0.0,
+                               false, rowscale, weights, ws.pmean, ws.mc));
+      cov_pointwise_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(k, dXs + c0 * d, dXs + c0 * d, d,
+                                                                                 mcur, ws.kss);
+      c->launches++;
+    }
+    GPRC_CHECK(variance_pass(c, F, ws, mpad, nullptr, 0));
+    finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
+        ws.pmean, ws.mc, (int)(F.n_pad / CT), ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, dmean + c0,
+        dvar + c0);
+    c->launches++;
+    GPRC_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// same with K_star (n x m) and kss (m) given on the host (closure kernels)
+static int predict_precomputed(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, const double* weights,
+                               const double* rowscale, const double* Ks, const double* kss, long m, double* mean,
+                               double* var) {
+  GPRC_CHECK(ensure_inverse(c, F));
+  GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
+  double *dmean = nullptr, *dvar = nullptr;
+  GPRC_CHECK(dmalloc(&dmean, (size_t)ws.mc));
+  GPRC_CHECK(dmalloc(&dvar, (size_t)ws.mc));
+  int rc = 0;
+  for (long c0 = 0; c0 < m && rc == 0; c0 += ws.mc) {
+    const long mcur = std::min(ws.mc, m - c0);
+    const long mpad = round_up(mcur, NB);
+    cudaMemsetAsync(ws.Ks, 0, sizeof(double) * F.n_pad * mpad, c->stream);
+    cudaMemcpy2DAsync(ws.Ks, F.n_pad * sizeof(double), Ks + c0 * F.n, F.n * sizeof(double), F.n * sizeof(double), mcur,
+                      cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(ws.kss, kss + c0, sizeof(double) * mcur, cudaMemcpyHostToDevice, c->stream);
+    gemv_t_rect_kernel<<<(unsigned)((mcur + 7) / 8), 256, 0, c->stream>>>(ws.Ks, F.n_pad, F.n, mcur, weights, dmean);
+    c->launches++;
+    if (rowscale) {
+      scale_rows_kernel<<<grid2(F.n, mcur), 256, 0, c->stream>>>(ws.Ks, F.n_pad, F.n, mcur, rowscale);
+      c->launches++;
+    }
+    if ((rc = variance_pass(c, F, ws, mpad, nullptr, 0))) break;
+    finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
+        nullptr, 0, 0, ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, nullptr, dvar);
+    c->launches++;
+    cudaMemcpyAsync(mean + c0, dmean, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(var + c0, dvar, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  }
+  dfree(dmean);
+  dfree(dvar);
+  return rc;
+}
+
+static int download_lower(gprc_ctx* c, const double* dM, long n, long ld, double* host) {
+  double* tmp = nullptr;
+  // stream the columns in slabs so that the staging buffer stays small
+  const long slab = std::max<long>(1, std::min<long>(n, (256L << 20) / 8 / std::max<long>(n, 1)));
+  GPRC_CHECK(dmalloc(&tmp, (size_t)n * slab));
+  int rc = 0;
+  for (long j0 = 0; j0 < n; j0 += slab) {
+    const long nc = std::min(slab, n - j0);
+    tril_slab_kernel<<<grid2(n, nc), 256, 0, c->stream>>>(dM, ld, n, j0, nc, tmp);
+    c->launches++;
+    cudaMemcpyAsync(host + j0 * n, tmp, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+      break;
+    }
+  }
+  dfree(tmp);
+  return rc;
+}
+
+// host K (n x n) -> padded device square with diag_add on the diagonal
+static int upload_square_padded(gprc_ctx* c, const double* hostK, long n, double* dst, long n_pad, double diag_add,
+                                bool pad_identity) {
+  double* stage = nullptr;
+  const long slab = std::max<long>(1, std::min<long>(n_pad, (256L << 20) / 8 / std::max<long>(n, 1)));
+  GPRC_CHECK(dmalloc(&stage, (size_t)n * slab));
+  int rc = 0;
+  for (long j0 = 0; j0 < n_pad; j0 += slab) {
+    const long nc = std::min(slab, n_pad - j0);
+    const long ncv = std::max<long>(0, std::min(nc, n - j0));
+    if (ncv > 0) cudaMemcpyAsync(stage, hostK + j0 * n, sizeof(double) * n * ncv, cudaMemcpyHostToDevice, c->stream);
+    place_slab_kernel<<<grid2(n_pad, nc), 256, 0, c->stream>>>(stage, n, j0, ncv, dst, n_pad, n_pad, nc, diag_add,
+                                                               pad_identity ? 1 : 0);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);  // the staging buffer is reused by the next slab
+    if (e != cudaSuccess) {
+      rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+      break;
+    }
+  }
+  dfree(stage);
+  return rc;
+}
+
+// =================================================================================================================
+// (2)+(3) GPR
+// =================================================================================================================
+static void gpr_destroy(gprc_gpr* g) {
+  if (!g) return;
+  dfree(g->X);
+  dfree(g->y);
+  dfree(g->alpha);
+  g->F.release();
+  g->ws.release();
+  delete g;
+}
+
+// K (+ noise I, identity padding) is already in g->F.L; factor, solve, reduce.
+static int gpr_finish_fit(gprc_ctx* c, gprc_gpr* g, double* logp, long* info) {
+  FactorState& F = g->F;
+  GPRC_CHECK(factor_run(c, F, info));
+  if (*info != 0) return 0;
+  double *work = nullptr, *tmp = nullptr;
+  GPRC_CHECK(dmalloc(&work, (size_t)F.n_pad));
+  GPRC_CHECK(dmalloc(&tmp, (size_t)F.n_pad));
+  int rc = 0;
+  {
+    PhaseTimer t(c, GPRC_T_SOLVE);
+    rc = potrs_vec(c, F.L, F.n_pad, F.n_pad, F.dinv, g->y, work, tmp, g->alpha);
+    if (rc == 0) {
+      gp_reduce_kernel<<<1, 1024, 0, c->stream>>>(g->y, g->alpha, F.diag, F.n, c->d_scalars);
+      c->launches++;
+    }
+  }
+  if (rc == 0) {
+    cudaMemcpyAsync(c->h_scalars, c->d_scalars, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  }
+  dfree(work);
+  dfree(tmp);
+  if (rc) return rc;
+  // -0.5 * y %*% alpha - sum(log(diag(L))) - n / 2 * log(2 * pi)        R/GPRclass.R:153
+  g->logp = -0.5 * c->h_scalars[0] - c->h_scalars[1] - (double)F.n / 2.0 * log(2.0 * M_PI);
+  if (logp) *logp = g->logp;
+  return 0;
+}
+
+static int gpr_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, bool x_on_device, int d, long n,
+                          const double* y, bool y_on_device, const double* Kpre, double noise, gprc_gpr** out,
+                          double* logp, long* info, double* min_leading_logdet) {
+  GPRC_ARG(c && out && info && y && n > 0 && noise >= 0.0);
+  GPRC_ARG(Kpre != nullptr || (k != nullptr && X != nullptr && d > 0));
+  *out = nullptr;
+  *info = 0;
+  DeviceGuard guard(c->device);
+  gprc_gpr* g = new gprc_gpr();
+  g->ctx = c;
+  g->d = d;
+  g->noise = noise;
+  g->precomputed = (Kpre != nullptr);
+  int rc = 0;
+  do {
+    if ((rc = factor_alloc(g->F, n))) break;
+    FactorState& F = g->F;
+    if ((rc = dmalloc(&g->y, (size_t)F.n_pad))) break;
+    if ((rc = dmalloc(&g->alpha, (size_t)F.n_pad))) break;
+    cudaMemsetAsync(g->y, 0, sizeof(double) * F.n_pad, c->stream);
+    cudaMemcpyAsync(g->y, y, sizeof(double) * n, y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                    c->stream);
+    if (Kpre) {
+      // K + new_noise * diag(n) with K supplied by the host (closure kernels, R/GPRclass.R:133,142)
+      PhaseTimer t(c, GPRC_T_BUILD_K);
+      rc = upload_square_padded(c, Kpre, n, F.L, F.n_pad, noise, true);
+    } else {
+      if ((rc = make_spec(c, k, d, g->spec))) break;
+      g->khost = *k;
+      if ((rc = dmalloc(&g->X, (size_t)d * n))) break;
+      cudaMemcpyAsync(g->X, X, sizeof(double) * d * n, x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                      c->stream);
+      PhaseTimer t(c, GPRC_T_BUILD_K);
+      rc = cov_build_dev(c, g->spec.dev, g->X, d, n, g->X, n, F.L, F.n_pad, F.n_pad, F.n_pad, true, true, noise, true,
+                         nullptr, nullptr, nullptr, 0);
+    }
+    if (rc) break;
+    if ((rc = gpr_finish_fit(c, g, logp, info))) break;
+    if (min_leading_logdet && *info == 0) *min_leading_logdet = c->h_scalars[3];
+  } while (0);
+  if (rc != 0 || *info != 0) {
+    cudaStreamSynchronize(c->stream);
+    gpr_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return 0;
+}
+
+extern "C" int gprc_gpr_fit(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                            double noise, gprc_gpr** out, double* logp, long* info) {
+  return gpr_fit_common(c, k, X, false, d, n, y, false, nullptr, noise, out, logp, info, nullptr);
+}
+extern "C" int gprc_gpr_fit_dev(gprc_ctx* c, const gprc_kernel* k, const double* dX, int d, long n, const double* dy,
+                                double noise, gprc_gpr** out, double* logp, long* info) {
+  return gpr_fit_common(c, k, dX, true, d, n, dy, true, nullptr, noise, out, logp, info, nullptr);
+}
+extern "C" int gprc_gpr_fit_precomputed(gprc_ctx* c, const double* K, long n, const double* y, double noise,
+                                        gprc_gpr** out, double* logp, long* info) {
+  GPRC_ARG(K != nullptr);
+  return gpr_fit_common(c, nullptr, nullptr, false, 0, n, y, false, K, noise, out, logp, info, nullptr);
+}
+
+extern "C" int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, double* dmean, double* dvar) {
+  GPRC_ARG(g && dXs && dmean && dvar && m >= 0);
+  GPRC_ARG(!g->precomputed);
+  if (m == 0) return 0;
+  DeviceGuard guard(g->ctx->device);
+  return predict_pointwise_dev(g->ctx, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar);
+}
+
+extern "C" int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* mean, double* var) {
+  GPRC_ARG(g && Xs && mean && var && m >= 0);
+  GPRC_ARG(!g->precomputed);
+  if (m == 0) return 0;
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c->device);
+  double *dXs = nullptr, *dmean = nullptr, *dvar = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dXs, (size_t)g->d * m))) break;
+    if ((rc = dmalloc(&dmean, (size_t)m))) break;
+    if ((rc = dmalloc(&dvar, (size_t)m))) break;
+    cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar)))
+      break;
+    cudaMemcpyAsync(mean, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(var, dvar, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dXs);
+  dfree(dmean);
+  dfree(dvar);
+  return rc;
+}
+
+extern "C" int gprc_gpr_predict_precomputed(gprc_gpr* g, const double* Ks, const double* kss, long m, double* mean,
+                                            double* var) {
+  GPRC_ARG(g && Ks && kss && mean && var && m >= 0);
+  if (m == 0) return 0;
+  DeviceGuard guard(g->ctx->device);
+  return predict_precomputed(g->ctx, g->F, g->ws, g->alpha, nullptr, Ks, kss, m, mean, var);
+}
+
+// predict(X_star, pointwise_var = FALSE): Sigma = covariance_matrix(X_star, X_star, k) - t(v) %*% v   R/GPRclass.R:167
+extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, double* mean, double* cov) {
+  GPRC_ARG(g && Xs && mean && cov && m > 0);
+  GPRC_ARG(!g->precomputed);
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c->device);
+  FactorState& F = g->F;
+  const long mp = round_up(m, NB);
+  GPRC_CHECK(ensure_inverse(c, F));
+  PredictWorkspace ws;  // private workspace sized for the whole set (V^T must be complete before the product)
+  double *dXs = nullptr, *dmean = nullptr, *dVt = nullptr, *dS = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&ws.Ks, (size_t)F.n_pad * mp))) break;
+    if ((rc = dmalloc(&ws.pmean, (size_t)(F.n_pad / CT) * mp))) break;
+    if ((rc = dmalloc(&ws.pvar, (size_t)(F.n_pad / NB) * mp))) break;
+    if ((rc = dmalloc(&ws.kss, (size_t)mp))) break;
+    ws.mc = mp;
+    if ((rc = dmalloc(&dXs, (size_t)g->d * m))) break;
+    if ((rc = dmalloc(&dmean, (size_t)mp))) break;
+    if ((rc = dmalloc(&dVt, (size_t)mp * F.n_pad))) break;
+    if ((rc = dmalloc(&dS, (size_t)mp * mp))) break;
+    cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
+    {
+      PhaseTimer t(c, GPRC_T_BUILD_KS);
+      if ((rc = cov_build_dev(c, g->spec.dev, g->X, g->d, F.n, dXs, m, ws.Ks, F.n_pad, F.n_pad, mp, false, false, 0.0,
+                              false, nullptr, g->alpha, ws.pmean, ws.mc)))
+        break;
+      // Sigma starts as covariance_matrix(X_star, X_star, k); zero padding
+      if ((rc = cov_build_dev(c, g->spec.dev, dXs, g->d, m, dXs, m, dS, mp, mp, mp, false, false, 0.0, false, nullptr,
+                              nullptr, nullptr, 0)))
+        break;
+    }
+    if ((rc = variance_pass(c, F, ws, mp, dVt, mp))) break;
+    finalize_predict_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(
+        ws.pmean, ws.mc, (int)(F.n_pad / CT), nullptr, 0, 0, nullptr, m, dmean, nullptr);
+    c->launches++;
+    {
+      // Sigma -= V^T V  with V^T stored m_pad x n_pad (test point contiguous): C = C - A A^T
+      PhaseTimer t(c, GPRC_T_VAR);
+      DgemmPolicy<false> p;
+      p.A = dVt;
+      p.lda = mp;
+      p.B = dVt;
+      p.ldb = mp;
+      p.C = dS;
+      p.ldc = mp;
+      p.alpha = -1.0;
+      p.beta = 1.0;
+      p.K = (int)F.n_pad;
+      p.tiles_m = (int)(mp / NB);
+      if ((rc = launch_gemm(c, p, dim3((unsigned)((mp / NB) * (mp / NB)))))) break;
+    }
+    cudaMemcpyAsync(mean, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpy2DAsync(cov, m * sizeof(double), dS, mp * sizeof(double), m * sizeof(double), m, cudaMemcpyDeviceToHost,
+                      c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  ws.release();
+  dfree(dXs);
+  dfree(dmean);
+  dfree(dVt);
+  dfree(dS);
+  return rc;
+}
+
+extern "C" int gprc_gpr_get(gprc_gpr* g, int what, double* host) {
+  GPRC_ARG(g && host);
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c->device);
+  switch (what) {
+    case GPRC_GET_L: return download_lower(c, g->F.L, g->F.n, g->F.n_pad, host);
+    case GPRC_GET_LINV:
+      GPRC_CHECK(ensure_inverse(c, g->F));
+      return download_lower(c, g->F.W, g->F.n, g->F.n_pad, host);
+    case GPRC_GET_ALPHA: return gprc_dev_d2h(c, host, g->alpha, sizeof(double) * g->F.n);
+    default: return set_error(-1, __FILE__, __LINE__, "gprc_gpr_get: unknown item");
+  }
+}
+extern "C" long gprc_gpr_n(const gprc_gpr* g) { return g ? g->F.n : 0; }
+extern "C" void gprc_gpr_free(gprc_gpr* g) {
+  if (!g) return;
+  DeviceGuard guard(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  gpr_destroy(g);
+}
+
+// =================================================================================================================
+// fit(): dens / dens_deriv
+// =================================================================================================================
+extern "C" int gprc_logml(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                          double noise, double* logp, double* min_leading_logdet, long* info) {
+  GPRC_ARG(logp && info);
+  gprc_gpr* g = nullptr;
+  GPRC_CHECK(gpr_fit_common(c, k, X, false, d, n, y, false, nullptr, noise, &g, logp, info, min_leading_logdet));
+  if (g) gprc_gpr_free(g);
+  return 0;
+}
+
+extern "C" int gprc_logml_batch(gprc_ctx* c, const gprc_kernel* specs, int nspec, const double* X, int d, long n,
+                                const double* y, double noise, double* logp, double* min_leading_logdet, long* info) {
+  GPRC_ARG(c && specs && nspec >= 0 && X && y && logp && info && n > 0 && d > 0);
+  DeviceGuard guard(c->device);
+  // X and y are uploaded once; every evaluation reuses them on the device
+  double *dX = nullptr, *dy = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dX, (size_t)d * n))) break;
+    if ((rc = dmalloc(&dy, (size_t)n))) break;
+    cudaMemcpyAsync(dX, X, sizeof(double) * d * n, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+    for (int s = 0; s < nspec && rc == 0; ++s) {
+      gprc_gpr* g = nullptr;
+      double lp = 0.0, ml = 0.0;
+      long inf = 0;
+      rc = gpr_fit_common(c, &specs[s], dX, true, d, n, dy, true, nullptr, noise, &g, &lp, &inf, &ml);
+      logp[s] = (inf == 0) ? lp : NAN;
+      if (min_leading_logdet) min_leading_logdet[s] = (inf == 0) ? ml : NAN;
+      info[s] = inf;
+      if (g) gprc_gpr_free(g);
+    }
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  dfree(dX);
+  dfree(dy);
+  return rc;
+}
+
+// ---- dens_deriv, R/fit.R:126-139 ---------------------------------------------------------------------------------
+namespace gprc {
+// d k / d v[0], d k / d v[1] for one pair.  textbook != 0: derivative of the kernel w.r.t. the optimiser's parameter
+// vector v in the kernel's own positional order (sqrexp (l); gammaexp (l, gamma); rationalquadratic (l, alpha);
+// polynomial (sigma, p)).  textbook == 0: the reference's cov_dict[[*]]$deriv called positionally with v, which for
+// gammaexp / rationalquadratic reads v[0] as gamma / alpha and v[1] as l (R/fit.R:10,25 vs R/GPRclass.R:397,401; A.6).
+__device__ __forceinline__ void kderiv(int id, int textbook, double v0, double v1, double s /* r2 or dot */,
+                                       double& d0, double& d1) {
+  d0 = d1 = 0.0;
+  if (id == GPRC_SQREXP) {  // r^2/l^3 * exp(-r^2/(l^2 * 2))                                      R/fit.R:4-7
+    const double l = v0;
+    d0 = s / (l * l * l) * exp(-s / (l * l * 2.0));
+  } else if (id == GPRC_POLYNOMIAL) {  // c(p (x.y + sigma)^(p-1), (x.y + sigma)^p log(x.y + sigma))  R/fit.R:20-22
+    const double b = s + v0, p = v1;
+    d0 = p * pow(b, p - 1.0);
+    d1 = pow(b, p) * log(b);
+  } else if (id == GPRC_GAMMAEXP) {
+    const double r = sqrt(s);
+    if (textbook) {
+      const double l = v0, g = v1, q = pow(r / l, g), e = exp(-q);
+      d0 = e * g * q / l;
+      d1 = (r > 0.0) ? -e * q * log(r / l) : 0.0;
+    } else {  // deriv(x, y, gamma = v[0], l = v[1])                                               R/fit.R:10-13
+      const double g = v0, l = v1, q = pow(r / l, g), e = exp(-q);
+      d0 = -e * q * log(r / l);  // NaN at r = 0, exactly like R (0 * -Inf)
+      d1 = e * g * pow(r, g) / pow(l, g + 1.0);
+    }
+  } else if (id == GPRC_RATQUAD) {
+    if (textbook) {
+      const double l = v0, a = v1, base = 1.0 + s / (2.0 * a * l * l);
+      d0 = s / (l * l * l) * pow(base, -a - 1.0);
+      d1 = pow(base, -a) * (-log(base) + s / (2.0 * a * l * l * base));
+    } else {  // deriv(x, y, alpha = v[0], l = v[1])                                                R/fit.R:25-31
+      const double a = v0, l = v1, t = 2.0 * l * l * a, base = s / t + 1.0;
+      d0 = (pow(base, -a) * (s - (t + s) * log(base))) / (t + s);
+      d1 = (s * pow(base, -a - 1.0)) / (l * l * l);
+    }
+  }
+}
+
+// dK0, dK1 (n_pad x n_pad, zero padding) for all pairs of columns of X
+__global__ void __launch_bounds__(256) dk_tile_kernel(int id, int textbook, double v0, double v1,
+                                                      const double* __restrict__ X, int d, long n, long n_pad,
+                                                      double* __restrict__ dK0, double* __restrict__ dK1) {
+  const long i = blockIdx.x * 16L + (threadIdx.x & 15), j = blockIdx.y * 16L + (threadIdx.x >> 4);
+  if (i >= n_pad || j >= n_pad) return;
+  double d0 = 0.0, d1 = 0.0;
+  if (i < n && j < n) {
+    double s = 0.0;
+    const bool dist = (id != GPRC_POLYNOMIAL);
+    for (int dd = 0; dd < d; ++dd) {
+      const double a = X[i * d + dd], b = X[j * d + dd];
+      s = dist ? __dadd_rn(s, __dmul_rn(a - b, a - b)) : __dadd_rn(s, __dmul_rn(a, b));
+    }
+    kderiv(id, textbook, v0, v1, s, d0, d1);
+  }
+  dK0[i + j * n_pad] = d0;
+  if (dK1) dK1[i + j * n_pad] = d1;
+}
+// out[k] = sum_{i >= k} W[i, k]^2 = (L^-T L^-1)_kk : warp per column
+__global__ void __launch_bounds__(256) colnorm2_lower_kernel(const double* __restrict__ W, long ld, long n,
+                                                             double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= n) return;
+  const double* Wp = W + col * ld;
+  double s = 0.0;
+  for (long i = col + lane; i < n; i += 32) s = fma(Wp[i], Wp[i], s);
+  s = warp_sum(s);
+  if (lane == 0) out[col] = s;
+}
+// single-CTA reductions: mode 0: out = 0.5 * sum_k (alpha_k^2 - kd_k) rs_k ; mode 1: out = sum_k a_k b_k
+__global__ void __launch_bounds__(1024) grad_reduce_kernel(int mode, const double* __restrict__ a,
+                                                           const double* __restrict__ b, const double* __restrict__ c,
+                                                           long n, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  const int tid = threadIdx.x;
+  const long chunk = (n + 1023) / 1024;
+  const long lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+  double s = 0.0;
+  for (long i = lo; i < hi; ++i) s += (mode == 0) ? (a[i] * a[i] - b[i]) * c[i] : a[i] * b[i];
+  sh[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 1024; ++q) t += sh[q];
+    out[0] = (mode == 0) ? 0.5 * t : t;
+  }
+}
+// out[0] = sum_{j} sum_{i >= j} W[i + j ld] Z[i + j ld]   (tr(W^T Z) for lower-triangular W); one CTA, fixed order
+__global__ void __launch_bounds__(1024) tril_dot_kernel(const double* __restrict__ W, const double* __restrict__ Z,
+                                                        long ld, long n, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  for (long j = 0; j < n; ++j)
+    for (long i = j + tid; i < n; i += 1024) s = fma(W[i + j * ld], Z[i + j * ld], s);
+  sh[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 1024; ++q) t += sh[q];
+    out[0] = t;
+  }
+}
+}  // namespace gprc
+
+extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                               double noise, int formula, double* grad, int nparam, long* info) {
+  GPRC_ARG(c && k && X && y && grad && info && n > 0 && d > 0);
+  GPRC_ARG(k->id == GPRC_SQREXP || k->id == GPRC_GAMMAEXP || k->id == GPRC_RATQUAD || k->id == GPRC_POLYNOMIAL);
+  const int np_expected = (k->id == GPRC_SQREXP) ? 1 : 2;
+  GPRC_ARG(nparam == np_expected);
+  const int textbook = (formula == GPRC_GRAD_TEXTBOOK);
+  double v0, v1 = 0.0;
+  switch (k->id) {
+    case GPRC_SQREXP: v0 = k->l; break;
+    case GPRC_GAMMAEXP: v0 = k->l; v1 = k->gamma; break;
+    case GPRC_RATQUAD: v0 = k->l; v1 = k->alpha; break;
+    default: v0 = k->sigma; v1 = k->p; break;
+  }
+  // as coded the reference inverts the NOISE-FREE K (R/fit.R:136); the textbook formula uses K + noise I
+  gprc_gpr* g = nullptr;
+  GPRC_CHECK(gpr_fit_common(c, k, X, false, d, n, y, false, nullptr, textbook ? noise : 0.0, &g, nullptr, info,
+                            nullptr));
+  if (*info != 0 || !g) return 0;
+  DeviceGuard guard(c->device);
+  FactorState& F = g->F;
+  const long np = F.n_pad;
+  double *dK0 = nullptr, *dK1 = nullptr, *vec = nullptr, *ones = nullptr, *Z = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = ensure_inverse(c, F))) break;
+    if ((rc = dmalloc(&dK0, (size_t)np * np))) break;
+    if (nparam > 1 && (rc = dmalloc(&dK1, (size_t)np * np))) break;
+    if ((rc = dmalloc(&vec, (size_t)np * 2)) || (rc = dmalloc(&ones, (size_t)np))) break;
+    dk_tile_kernel<<<dim3((unsigned)(np / 16), (unsigned)(np / 16)), 256, 0, c->stream>>>(k->id, textbook, v0, v1, g->X,
+                                                                                         d, n, np, dK0, dK1);
+    c->launches++;
+    double* dKs[2] = {dK0, dK1};
+    if (!textbook) {
+      fill_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(ones, np, 1.0);
+      colnorm2_lower_kernel<<<(unsigned)((np + 7) / 8), 256, 0, c->stream>>>(F.W, np, n, vec);  // diag(K^-1)
+      c->launches += 2;
+      for (int p = 0; p < nparam && rc == 0; ++p) {
+        rc = gemv_t(c, dKs[p], np, np, ones, vec + np);  // row sums of dK_p (symmetric)
+        grad_reduce_kernel<<<1, 1024, 0, c->stream>>>(0, g->alpha, vec, vec + np, n, c->d_scalars + p);
+        c->launches++;
+      }
+    } else {
+      if ((rc = dmalloc(&Z, (size_t)np * np))) break;
+      for (int p = 0; p < nparam && rc == 0; ++p) {
+        // quad = alpha' dK alpha ; trace = tr(Ky^-1 dK) = tr(W^T (W dK))
+        if ((rc = gemv_t(c, dKs[p], np, np, g->alpha, vec))) break;
+        grad_reduce_kernel<<<1, 1024, 0, c->stream>>>(1, g->alpha, vec, nullptr, n, c->d_scalars + 8 + p);
+        DgemmPolicy<true> pol{F.W, np, dKs[p], np, Z, np, 1.0, 0.0, (int)np, (int)(np / NB)};
+        if ((rc = launch_gemm(c, pol, dim3((unsigned)((np / NB) * (np / NB)))))) break;
+        tril_dot_kernel<<<1, 1024, 0, c->stream>>>(F.W, Z, np, n, c->d_scalars + 16 + p);
+        c->launches += 2;
+      }
+    }
+    if (rc) break;
+    cudaMemcpyAsync(c->h_scalars, c->d_scalars, 24 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+      break;
+    }
+    for (int p = 0; p < nparam; ++p)
+      grad[p] = textbook ? 0.5 * (c->h_scalars[8 + p] - c->h_scalars[16 + p]) : c->h_scalars[p];
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  dfree(dK0);
+  dfree(dK1);
+  dfree(vec);
+  dfree(ones);
+  dfree(Z);
+  gprc_gpr_free(g);
+  return rc;
+}
+
+// =================================================================================================================
+// (4) GPC: Laplace-approximation Newton loop, R/GPCclass.R:73-103
+// =================================================================================================================
+static void gpc_destroy(gprc_gpc* g) {
+  if (!g) return;
+  dfree(g->X);
+  dfree(g->y);
+  dfree(g->K);
+  dfree(g->f);
+  dfree(g->sw);
+  dfree(g->gradl);
+  g->F.release();
+  g->ws.release();
+  delete g;
+}
+
+static int gpc_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                          const double* Kpre, double eps, int guard, int max_iter, gprc_gpc** out, int* iters,
+                          double* trace, int trace_cap, double* sum_diagL, double* sum_log_diagL, int* status) {
+  GPRC_ARG(c && out && y && n > 0 && eps > 0.0 && iters && status);
+  GPRC_ARG(Kpre != nullptr || (k != nullptr && X != nullptr && d > 0));
+  *out = nullptr;
+  *iters = 0;
+  *status = 0;
+  DeviceGuard dg(c->device);
+  gprc_gpc* g = new gprc_gpc();
+  g->ctx = c;
+  g->d = d;
+  g->precomputed = (Kpre != nullptr);
+  double *bvec = nullptr, *Kb = nullptr, *cvec = nullptr, *tvec = nullptr, *avec = nullptr, *work = nullptr,
+         *tmp = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = factor_alloc(g->F, n))) break;
+    FactorState& F = g->F;
+    const long np = F.n_pad;
+    if ((rc = dmalloc(&g->y, (size_t)np)) || (rc = dmalloc(&g->f, (size_t)np)) || (rc = dmalloc(&g->sw, (size_t)np)) ||
+        (rc = dmalloc(&g->gradl, (size_t)np)) || (rc = dmalloc(&g->K, (size_t)np * np)) ||
+        (rc = dmalloc(&bvec, (size_t)np)) || (rc = dmalloc(&Kb, (size_t)np)) || (rc = dmalloc(&cvec, (size_t)np)) ||
+        (rc = dmalloc(&tvec, (size_t)np)) || (rc = dmalloc(&avec, (size_t)np)) || (rc = dmalloc(&work, (size_t)np)) ||
+        (rc = dmalloc(&tmp, (size_t)np)))
+      break;
+    cudaMemsetAsync(g->y, 0, sizeof(double) * np, c->stream);
+    cudaMemcpyAsync(g->y, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(g->f, 0, sizeof(double) * np, c->stream);  // f <- rep(0, n)              R/GPCclass.R:74
+    {
+      PhaseTimer t(c, GPRC_T_BUILD_K);
+      if (Kpre) {
+        if ((rc = upload_square_padded(c, Kpre, n, g->K, np, 0.0, false))) break;
+      } else {
+        if ((rc = make_spec(c, k, d, g->spec))) break;
+        if ((rc = dmalloc(&g->X, (size_t)d * n))) break;
+        cudaMemcpyAsync(g->X, X, sizeof(double) * d * n, cudaMemcpyHostToDevice, c->stream);
+        // K <- covariance_matrix(X, X, k): full symmetric (K %*% b needs both triangles), zero padding
+        if ((rc = cov_build_dev(c, g->spec.dev, g->X, d, n, g->X, n, g->K, np, np, np, false, false, 0.0, false,
+                                nullptr, nullptr, nullptr, 0)))
+          break;
+      }
+    }
+    const dim3 tgrid((unsigned)(np / 64), (unsigned)(np / 64));
+    const unsigned vgrid = (unsigned)((np + 255) / 256);
+    double last_objective = 0.0, least_objective = 0.0, objective = 0.0;
+    int it = 0;
+    PhaseTimer tn(c, GPRC_T_NEWTON);
+    while (true) {
+      ++it;
+      // P, W, B = I + sqrt(W) sqrt(W)' * K (fused), b = W f + (y + 1)/2 - P           R/GPCclass.R:78-81
+      gpc_build_B_kernel<<<tgrid, 256, 0, c->stream>>>(g->K, np, g->f, g->y, n, np, F.L, np, g->sw, bvec, nullptr);
+      c->launches++;
+      long info = 0;
+      if ((rc = factor_run(c, F, &info))) break;
+      if (info != 0) {
+        *status = 2;
+        break;
+      }
+      // intermediate <- solve(t(L), solve(L, sqrt(W) * (K %*% b)))                     R/GPCclass.R:82-83
+      if ((rc = gemv_t(c, g->K, np, np, bvec, Kb))) break;
+      vec_mul_kernel<<<vgrid, 256, 0, c->stream>>>(g->sw, Kb, np, cvec);
+      c->launches++;
+      if ((rc = potrs_vec(c, F.L, np, np, F.dinv, cvec, work, tmp, tvec))) break;
+      // a <- b - sqrt(W) * intermediate ; f <- K %*% a                                 R/GPCclass.R:84-85
+      gpc_a_kernel<<<vgrid, 256, 0, c->stream>>>(bvec, g->sw, tvec, np, avec);
+      c->launches++;
+      if ((rc = gemv_t(c, g->K, np, np, avec, g->f))) break;
+      gpc_objective_kernel<<<1, 1024, 0, c->stream>>>(avec, g->f, g->y, n, c->d_scalars);
+      c->launches++;
+      cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      cudaError_t e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) {
+        rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+        break;
+      }
+      objective = c->h_scalars[0];
+      if (trace && it <= trace_cap) trace[it - 1] = objective;
+      // stopping rule, literally R/GPCclass.R:87-96 (the guard is mis-signed in the reference: SURVEY.md A.2)
+      if (it > 1) {
+        if (fabs(objective - last_objective) < eps) {
+          break;
+        } else if (guard && least_objective + 10.0 < objective) {
+          *status = 1;
+          break;
+        }
+      } else {
+        least_objective = objective;
+      }
+      last_objective = objective;
+      if (max_iter > 0 && it >= max_iter) break;
+      if (!(objective == objective)) {  // NaN objective can never satisfy the rule: the reference would spin forever
+        *status = 2;
+        break;
+      }
+    }
+    *iters = it;
+    if (rc || *status != 0) break;
+    // P, W at f_hat; L <- t(chol(B)); logq pieces                                         R/GPCclass.R:99-103
+    gpc_build_B_kernel<<<tgrid, 256, 0, c->stream>>>(g->K, np, g->f, g->y, n, np, F.L, np, g->sw, bvec, g->gradl);
+    c->launches++;
+    long info = 0;
+    if ((rc = factor_run(c, F, &info))) break;
+    if (info != 0) {
+      *status = 2;
+      break;
+    }
+    gp_reduce_kernel<<<1, 1024, 0, c->stream>>>(nullptr, nullptr, F.diag, n, c->d_scalars);
+    c->launches++;
+    cudaMemcpyAsync(c->h_scalars, c->d_scalars, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+      break;
+    }
+    if (sum_log_diagL) *sum_log_diagL = c->h_scalars[1];
+    if (sum_diagL) *sum_diagL = c->h_scalars[2];
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  dfree(bvec);
+  dfree(Kb);
+  dfree(cvec);
+  dfree(tvec);
+  dfree(avec);
+  dfree(work);
+  dfree(tmp);
+  if (rc != 0 || *status != 0) {
+    gpc_destroy(g);
+    return rc;
+  }
+  dfree(g->K);  // predict_class only needs X, f_hat, sqrt(W) and the factor
+  g->K = nullptr;
+  *out = g;
+  return 0;
+}
+
+extern "C" int gprc_gpc_fit(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                            double eps, int guard, int max_iter, gprc_gpc** out, int* iters, double* objective_trace,
+                            int trace_cap, double* sum_diagL, double* sum_log_diagL, int* status) {
+  return gpc_fit_common(c, k, X, d, n, y, nullptr, eps, guard, max_iter, out, iters, objective_trace, trace_cap,
+                        sum_diagL, sum_log_diagL, status);
+}
+extern "C" int gprc_gpc_fit_precomputed(gprc_ctx* c, const double* K, long n, const double* y, double eps, int guard,
+                                        int max_iter, gprc_gpc** out, int* iters, double* objective_trace,
+                                        int trace_cap, double* sum_diagL, double* sum_log_diagL, int* status) {
+  GPRC_ARG(K != nullptr);
+  return gpc_fit_common(c, nullptr, nullptr, 0, n, y, K, eps, guard, max_iter, out, iters, objective_trace, trace_cap,
+                        sum_diagL, sum_log_diagL, status);
+}
+
+// fs_bar <- t(K_star) %*% ((y + 1)/2 - P); v <- solve(L, sqrt(W) * K_star); Vfs <- k(X*, X*) - colSums(v * v)
+// R/GPCclass.R:110-115
+extern "C" int gprc_gpc_predict_latent(gprc_gpc* g, const double* Xs, long m, double* fs_bar, double* Vfs) {
+  GPRC_ARG(g && Xs && fs_bar && Vfs && m >= 0);
+  GPRC_ARG(!g->precomputed);
+  if (m == 0) return 0;
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c->device);
+  double *dXs = nullptr, *dmean = nullptr, *dvar = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dXs, (size_t)g->d * m))) break;
+    if ((rc = dmalloc(&dmean, (size_t)m))) break;
+    if ((rc = dmalloc(&dvar, (size_t)m))) break;
+    cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar)))
+      break;
+    cudaMemcpyAsync(fs_bar, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(Vfs, dvar, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dXs);
+  dfree(dmean);
+  dfree(dvar);
+  return rc;
+}
+extern "C" int gprc_gpc_predict_latent_precomputed(gprc_gpc* g, const double* Ks, const double* kss, long m,
+                                                   double* fs_bar, double* Vfs) {
+  GPRC_ARG(g && Ks && kss && fs_bar && Vfs && m >= 0);
+  if (m == 0) return 0;
+  DeviceGuard guard(g->ctx->device);
+  return predict_precomputed(g->ctx, g->F, g->ws, g->gradl, g->sw, Ks, kss, m, fs_bar, Vfs);
+}
+extern "C" int gprc_gpc_get(gprc_gpc* g, int what, double* host) {
+  GPRC_ARG(g && host);
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c->device);
+  switch (what) {
+    case GPRC_GET_L: return download_lower(c, g->F.L, g->F.n, g->F.n_pad, host);
+    case GPRC_GET_FHAT: return gprc_dev_d2h(c, host, g->f, sizeof(double) * g->F.n);
+    case GPRC_GET_SQRTW: return gprc_dev_d2h(c, host, g->sw, sizeof(double) * g->F.n);
+    default: return set_error(-1, __FILE__, __LINE__, "gprc_gpc_get: unknown item");
+  }
+}
+extern "C" long gprc_gpc_n(const gprc_gpc* g) { return g ? g->F.n : 0; }
+extern "C" void gprc_gpc_free(gprc_gpc* g) {
+  if (!g) return;
+  DeviceGuard guard(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  gpc_destroy(g);
+}
+
+// =================================================================================================================
+// raw device primitives
+// =================================================================================================================
+extern "C" int gprc_dev_potrf(gprc_ctx* c, double* dA, long n, long ld, double* dinv, long* info) {
+  GPRC_ARG(c && dA && dinv && info && n > 0 && n % NB == 0 && ld % NB == 0 && ld >= n);
+  DeviceGuard guard(c->device);
+  *c->h_info = LONG_MAX;
+  GPRC_CUDA(cudaMemcpyAsync(c->d_info, c->h_info, sizeof(long), cudaMemcpyHostToDevice, c->stream));
+  {
+    PhaseTimer t(c, GPRC_T_CHOL);
+    GPRC_CHECK(potrf_blocked(c, dA, n, ld, dinv, c->d_info, nullptr));
+  }
+  GPRC_CUDA(cudaMemcpyAsync(c->h_info, c->d_info, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  *info = (*c->h_info == LONG_MAX) ? 0 : *c->h_info;
+  return 0;
+}
+
+extern "C" int gprc_dev_dgemm(gprc_ctx* c, int transb, long M, long N, long K, double alpha, const double* dA, long lda,
+                              const double* dB, long ldb, double beta, double* dC, long ldc) {
+  GPRC_ARG(c && dA && dB && dC && M > 0 && N > 0 && K >= 0);
+  GPRC_ARG(M % NB == 0 && N % NB == 0 && K % BK == 0 && lda % 2 == 0 && ldb % 2 == 0);
+  DeviceGuard guard(c->device);
+  const dim3 grid((unsigned)((M / NB) * (N / NB)));
+  if (transb) {
+    DgemmPolicy<false> p{dA, lda, dB, ldb, dC, ldc, alpha, beta, (int)K, (int)(M / NB)};
+    return launch_gemm(c, p, grid);
+  }
+  DgemmPolicy<true> p{dA, lda, dB, ldb, dC, ldc, alpha, beta, (int)K, (int)(M / NB)};
+  return launch_gemm(c, p, grid);
+}
+
+extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, const double* dinv, double* dW,
+                              double* dscratch) {
+  GPRC_ARG(c && dL && dinv && dW && dscratch && n > 0 && n % NB == 0 && ld % NB == 0 && ld >= n);
+  DeviceGuard guard(c->device);
+  PhaseTimer t(c, GPRC_T_TRTRI);
+  return trtri_levels(c, dL, n, ld, dinv, dW, dscratch);
+}

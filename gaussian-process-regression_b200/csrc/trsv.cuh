@@ -1,0 +1,178 @@
+// trsv.cuh -- the O(n^2), HBM-bound passes (north_star subsystem 3a): blocked triangular solves for
+// alpha = L^-T (L^-1 y) (R/GPRclass.R:152 -- the reference calls dense solve() twice, i.e. two LU factorisations;
+// here two substitutions), the symmetric GEMV of the GPC Newton step (R/GPCclass.R:82,85) and the reductions behind
+// logp (R/GPRclass.R:153), logq (R/GPCclass.R:103) and fit()'s leading-minor rule (R/fit.R:119).
+#pragma once
+#include "common.cuh"
+
+namespace gprc {
+
+constexpr int TRSV_ROWS = 512;  // rows of the rank-128 update per CTA
+
+// One block step of the forward substitution L x = b:
+//   x_j = Linv_j b_j   (every CTA, redundantly; CTA 0 stores it)
+//   b[rows below] -= L[rows, block j] x_j
+// b is the working right-hand side (blocks > j are updated in place), x receives the solution.
+__global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __restrict__ L, long ld,
+                                                            const double* __restrict__ dinv, int j, long n,
+                                                            double* __restrict__ b, double* __restrict__ x) {
+  __shared__ double bj[NB], xj[NB], part[NB];
+  const int tid = threadIdx.x, r = tid & (NB - 1), h = tid >> 7;
+  if (tid < NB) bj[tid] = b[(long)j * NB + tid];
+  __syncthreads();
+  const double* Li = dinv + (long)j * NB * NB;
+  double s = 0.0;
+#pragma unroll 8
+  for (int c = h * 64; c < h * 64 + 64; ++c) s = fma(Li[r + c * NB], bj[c], s);  // explicit zeros above the diagonal
+  if (h == 1) part[r] = s;
+  __syncthreads();
+  if (h == 0) xj[r] = s + part[r];
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
+  const long row0 = (long)(j + 1) * NB + (long)blockIdx.x * TRSV_ROWS;
+#pragma unroll
+  for (int q = 0; q < TRSV_ROWS / 256; ++q) {
+    const long row = row0 + q * 256 + tid;
+    if (row < n) {
+      const double* Lp = L + row + (long)j * NB * ld;
+      double acc = 0.0;
+#pragma unroll 16
+      for (int c = 0; c < NB; ++c) acc = fma(Lp[(long)c * ld], xj[c], acc);
+      b[row] -= acc;
+    }
+  }
+}
+
+// One block step of the backward substitution L^T x = b (j runs from the last block to the first):
+//   x_j = Linv_j^T b_j ;  b[k] -= sum_c L[j*128 + c, k] x_j[c]  for k < j*128
+// warp per column so that the 128 contiguous rows of a column of L are read coalesced.
+__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ L, long ld,
+                                                            const double* __restrict__ dinv, int j,
+                                                            double* __restrict__ b, double* __restrict__ x) {
+  __shared__ double bj[NB], xj[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < NB) bj[tid] = b[(long)j * NB + tid];
+  __syncthreads();
+  const double* Li = dinv + (long)j * NB * NB;
+  for (int r = warp; r < NB; r += 8) {  // x_j[r] = sum_{c >= r} Linv[c, r] b_j[c]
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      s = fma(Li[c + r * NB], bj[c], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) xj[r] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
+  if ((int)blockIdx.x >= j) return;         // j == 0: nothing left to update
+  const long col0 = (long)blockIdx.x * NB;  // this CTA updates columns [col0, col0 + 128), all < j * 128
+  const double* Lrow = L + (long)j * NB;
+  for (int kk = warp; kk < NB; kk += 8) {
+    const long k = col0 + kk;
+    const double* Lp = Lrow + k * ld;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane + 32 * q;
+      s = fma(Lp[c], xj[c], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) b[k] -= s;
+  }
+}
+
+// x = L^-T L^-1 rhs.  work: n doubles; rhs is left untouched.
+inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
+                     double* work, double* tmp, double* x) {
+  const int nt = (int)(n / NB);
+  GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int j = 0; j < nt; ++j) {
+    const long below = n - (long)(j + 1) * NB;
+    const unsigned grid = (unsigned)((below + TRSV_ROWS - 1) / TRSV_ROWS);
+    trsv_fwd_step_kernel<<<grid ? grid : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, n, work, tmp);
+    ctx->launches++;
+  }
+  for (int j = nt - 1; j >= 0; --j) {
+    trsv_bwd_step_kernel<<<j ? j : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, tmp, x);
+    ctx->launches++;
+  }
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+// only the forward half: x = L^-1 rhs
+inline int trsv_forward(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
+                        double* work, double* x) {
+  const int nt = (int)(n / NB);
+  GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int j = 0; j < nt; ++j) {
+    const long below = n - (long)(j + 1) * NB;
+    const unsigned grid = (unsigned)((below + TRSV_ROWS - 1) / TRSV_ROWS);
+    trsv_fwd_step_kernel<<<grid ? grid : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, n, work, x);
+    ctx->launches++;
+  }
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y = K^T v for a column-major n x n matrix (K symmetric in the callers): warp per column, coalesced.
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ K, long ld, long n,
+                                                     const double* __restrict__ v, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long col = (long)blockIdx.x * 8 + warp;
+  if (col >= n) return;
+  const double* Kp = K + col * ld;
+  double s = 0.0;
+  for (long i = lane; i < n; i += 32) s = fma(Kp[i], v[i], s);
+  s = warp_sum(s);
+  if (lane == 0) y[col] = s;
+}
+inline int gemv_t(gprc_ctx* ctx, const double* K, long ld, long n, const double* v, double* y) {
+  gemv_t_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(K, ld, n, v, y);
+  ctx->launches++;
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Reductions over the factor and the solution (single CTA, fixed order => reproducible):
+//   out[0] = sum_i y_i alpha_i            out[1] = sum_i log L_ii         out[2] = sum_i L_ii
+//   out[3] = min_i sum_{k<=i} 2 log L_kk  (log of the smallest leading-minor determinant, R/fit.R:119)
+__global__ void __launch_bounds__(1024) gp_reduce_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
+                                                         const double* __restrict__ diag, long n,
+                                                         double* __restrict__ out) {
+  __shared__ double s_dot[1024], s_log[1024], s_sum[1024], s_minpre[1024];
+  const int tid = threadIdx.x;
+  const long chunk = (n + 1023) / 1024;
+  const long lo = tid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+  double dot = 0.0, slog = 0.0, ssum = 0.0, minpre = INFINITY;
+  for (long i = lo; i < hi; ++i) {
+    if (y && alpha) dot = fma(y[i], alpha[i], dot);
+    if (diag) {
+      const double d = diag[i];
+      slog += log(d);
+      ssum += d;
+      minpre = fmin(minpre, 2.0 * slog);
+    }
+  }
+  s_dot[tid] = dot;
+  s_log[tid] = slog;
+  s_sum[tid] = ssum;
+  s_minpre[tid] = minpre;
+  __syncthreads();
+  if (tid == 0) {
+    double tdot = 0.0, tlog = 0.0, tsum = 0.0, tmin = INFINITY;
+    for (int t = 0; t < 1024; ++t) {
+      tmin = fmin(tmin, 2.0 * tlog + s_minpre[t]);  // prefix of earlier chunks + local min prefix
+      tdot += s_dot[t];
+      tlog += s_log[t];
+      tsum += s_sum[t];
+    }
+    out[0] = tdot;
+    out[1] = tlog;
+    out[2] = tsum;
+    out[3] = tmin;
+  }
+}
+
+}  // namespace gprc

@@ -1,0 +1,177 @@
+/*
+ * gprc.h -- C ABI of libgprc, the B200 (sm_100a) implementation of the Gaussian-process hot path of the R
+ * package `gprc` (MoHawastaken/Gaussian-Process-Regression).
+ *
+ * The reference has no FFI layer (pure R); these entry points are what a `.Call` shim
+ * (src/gprc_shim.c) binds so that R/GPRclass.R, R/GPCclass.R and R/fit.R keep their signatures.  Every function
+ * cites the reference lines it replaces.  Conventions:
+ *   - all matrices are column-major FP64 (R's layout); X is d x n with leading dimension d (points contiguous,
+ *     reference R/GPRclass.R:132,137);
+ *   - plain pointers and sizes only; the caller owns every host buffer, the library owns device memory behind the
+ *     opaque handles;
+ *   - return value: 0 = ok, < 0 = CUDA/argument error (text in gprc_last_error()); numerical failure is reported
+ *     LAPACK-style through `info` (> 0: 1-based index of the first non-positive pivot), never by a non-zero
+ *     return, so the host can run the reference's retry policy (R/GPRclass.R:141-149);
+ *   - functions ending in `_dev` take DEVICE pointers for the bulk arrays (bench "value" leg: inputs already in
+ *     HBM); all others take HOST pointers and include the copies.
+ *   - no CPU fallback exists: without a CUDA device gprc_ctx_create fails.
+ */
+#ifndef GPRC_H
+#define GPRC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gprc_ctx gprc_ctx; /* one device, one stream, workspaces, phase timers          */
+typedef struct gprc_gpr gprc_gpr; /* device: X, L (lower), L^-1 (lazy), alpha; host: logp      */
+typedef struct gprc_gpc gprc_gpc; /* device: X, K, f_hat, sqrt(W), L(B); host: objective trace */
+
+/* The six built-in kernels of R/GPRclass.R:381-403 plus "precomputed" for arbitrary R closures. */
+typedef enum {
+  GPRC_CONSTANT = 0,   /* k = c                                   R/GPRclass.R:382 */
+  GPRC_LINEAR = 1,     /* k = sum_d sigma_d x_d y_d               R/GPRclass.R:386 */
+  GPRC_POLYNOMIAL = 2, /* k = (x.y + sigma)^p                     R/GPRclass.R:390 */
+  GPRC_SQREXP = 3,     /* k = exp(-|x-y|^2 / (2 l^2))             R/GPRclass.R:394 */
+  GPRC_GAMMAEXP = 4,   /* k = exp(-(|x-y| / l)^gamma)             R/GPRclass.R:398 */
+  GPRC_RATQUAD = 5,    /* k = (1 + |x-y|^2 / (2 alpha l^2))^-alpha R/GPRclass.R:402 */
+  GPRC_PRECOMPUTED = 6
+} gprc_kernel_id;
+
+/* Parameters are NAMED, never positional (the reference mixes orders). */
+typedef struct {
+  int id; /* gprc_kernel_id */
+  double c, sigma, p, l, gamma, alpha;
+  const double* sigma_vec; /* HOST pointer; linear kernel with one sigma per dimension (R/GPRclass.R:298), or NULL */
+  int sigma_len;           /* 0 => scalar `sigma` is recycled (fit.R:17) */
+} gprc_kernel;
+
+/* flags for gprc_ctx_set_option */
+enum {
+  GPRC_OPT_GRAM_DMMA = 1 /* 1 (default): dot-product / norm-expansion builds use the FP64 tensor-core Gram tile
+                            kernel when d >= 4; 0: always direct differences as R/GPRclass.R:394 writes them */
+};
+
+/* what to fetch with gprc_gpr_get / gprc_gpc_get */
+enum {
+  GPRC_GET_L = 0,     /* n x n, lower, explicit zeros above the diagonal (R: t(chol(.)))   */
+  GPRC_GET_ALPHA = 1, /* n                                                                  */
+  GPRC_GET_LINV = 2,  /* n x n lower, L^-1 (forces the inversion)                           */
+  GPRC_GET_FHAT = 3,  /* n    (GPC)                                                         */
+  GPRC_GET_SQRTW = 4  /* n    (GPC)                                                         */
+};
+
+/* gradient formulas for gprc_logml_grad */
+enum {
+  GPRC_GRAD_AS_CODED = 0, /* fit.R:128-138 literally: noise-free K, 0.5*sum(diag(aa'-K^-1) %*% dK)  (A.5) */
+  GPRC_GRAD_TEXTBOOK = 1  /* 0.5 tr((aa' - Ky^-1) dK) with Ky = K + noise I (vignettes/gpr.Rmd:137)      */
+};
+
+/* phase timers (milliseconds, CUDA events on the library's stream; accumulated since gprc_ctx_reset_timers) */
+enum {
+  GPRC_T_BUILD_K = 0,   /* covariance_matrix(X, X, k) + noise       */
+  GPRC_T_CHOL = 1,      /* blocked Cholesky                         */
+  GPRC_T_SOLVE = 2,     /* alpha (two triangular solves) + logp     */
+  GPRC_T_TRTRI = 3,     /* L^-1                                     */
+  GPRC_T_BUILD_KS = 4,  /* K_star tiles + mean                      */
+  GPRC_T_VAR = 5,       /* v = L^-1 K_star with fused column norms  */
+  GPRC_T_NEWTON = 6,    /* GPC Newton loop                          */
+  GPRC_T_COUNT = 8
+};
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int gprc_ctx_create(gprc_ctx** out, int device);
+void gprc_ctx_free(gprc_ctx* ctx);
+int gprc_ctx_set_option(gprc_ctx* ctx, int option, int value);
+int gprc_ctx_sync(gprc_ctx* ctx);
+void gprc_ctx_reset_timers(gprc_ctx* ctx);
+int gprc_ctx_get_timers(gprc_ctx* ctx, double* ms /* GPRC_T_COUNT */, long* kernel_launches);
+const char* gprc_last_error(void);
+int gprc_version(void);
+
+/* ---- device memory helpers (bench / tests; the R shim never needs them) ---------------------------------- */
+int gprc_dev_malloc(gprc_ctx* ctx, void** dptr, unsigned long long bytes);
+int gprc_dev_free(gprc_ctx* ctx, void* dptr);
+int gprc_dev_h2d(gprc_ctx* ctx, void* dptr, const void* host, unsigned long long bytes);
+int gprc_dev_d2h(gprc_ctx* ctx, void* host, const void* dptr, unsigned long long bytes);
+int gprc_host_register(void* host, unsigned long long bytes);   /* pin an existing host buffer */
+int gprc_host_unregister(void* host);
+
+/* ---- (1) kernel-matrix build ----------------------------------------------------------------------------- */
+/* covariance_matrix(A, B, k), R/GPRclass.R:355-357.  out is nA x nB column-major (host). */
+int gprc_cov_matrix(gprc_ctx* ctx, const gprc_kernel* k, const double* A, int d, long nA, const double* B, long nB,
+                    double* out);
+/* k(A, B) applied column-wise to two d x n matrices: the `.matrix` contract, R/GPRclass.R:378-403. out: n (host). */
+int gprc_cov_pointwise(gprc_ctx* ctx, const gprc_kernel* k, const double* A, const double* B, int d, long n,
+                       double* out);
+
+/* ---- (2)+(3) GPR: K build, Cholesky of K + noise I, alpha, logp -- GPR$initialize, R/GPRclass.R:138-153 ----- */
+/* One attempt with the given noise; *info > 0 means chol() would have thrown: the host re-calls with the next
+ * noise of the schedule R/GPRclass.R:141-148.  On info > 0 no model is created (*out = NULL). */
+int gprc_gpr_fit(gprc_ctx* ctx, const gprc_kernel* k, const double* X, int d, long n, const double* y, double noise,
+                 gprc_gpr** out, double* logp, long* info);
+int gprc_gpr_fit_dev(gprc_ctx* ctx, const gprc_kernel* k, const double* dX, int d, long n, const double* dy,
+                     double noise, gprc_gpr** out, double* logp, long* info);
+/* k is an arbitrary closure evaluated by the host: K (n x n, no noise added yet) comes in precomputed. */
+int gprc_gpr_fit_precomputed(gprc_ctx* ctx, const double* K, long n, const double* y, double noise, gprc_gpr** out,
+                             double* logp, long* info);
+/* GPR$predict(X_star, pointwise_var = TRUE), R/GPRclass.R:155-165: mean (m), var (m). */
+int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* mean, double* var);
+int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, double* dmean, double* dvar);
+/* precomputed K_star (n x m) and kss = k(X_star, X_star) (m) for closure kernels */
+int gprc_gpr_predict_precomputed(gprc_gpr* g, const double* Ks, const double* kss, long m, double* mean, double* var);
+/* GPR$predict(X_star, pointwise_var = FALSE), R/GPRclass.R:167-168: mean (m), cov (m x m). */
+int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, double* mean, double* cov);
+int gprc_gpr_get(gprc_gpr* g, int what, double* host);
+long gprc_gpr_n(const gprc_gpr* g);
+void gprc_gpr_free(gprc_gpr* g);
+
+/* ---- fit(): log marginal likelihood and gradient -- dens / dens_deriv, R/fit.R:117-139 -------------------- */
+/* logp as fit.R:121-123.  min_leading_logdet = min_i log det((K + noise I)[1:i,1:i]) = min prefix sum of
+ * 2 log L_ii, so the host can apply the literal fit.R:119 rule (det underflow) or the
+ * Cholesky-success rule.  info > 0: not positive definite. */
+int gprc_logml(gprc_ctx* ctx, const gprc_kernel* k, const double* X, int d, long n, const double* y, double noise,
+               double* logp, double* min_leading_logdet, long* info);
+/* nparam gradient entries in the order of the reference's `v` (the optimiser's parameter vector, fit.R:118):
+ * sqrexp (l); gammaexp (l, gamma); rationalquadratic (l, alpha); polynomial (sigma, p). */
+int gprc_logml_grad(gprc_ctx* ctx, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                    double noise, int formula, double* grad, int nparam, long* info);
+/* nspec independent evaluations (multi-start / grid), the unit that shards across GPUs. */
+int gprc_logml_batch(gprc_ctx* ctx, const gprc_kernel* specs, int nspec, const double* X, int d, long n,
+                     const double* y, double noise, double* logp, double* min_leading_logdet, long* info);
+
+/* ---- (4) GPC: Laplace-approximation Newton loop -- GPC$initialize, R/GPCclass.R:73-103 ------------------ */
+/* guard != 0 applies the reference's divergence rule R/GPCclass.R:90 literally; when it fires
+ * the return value is 0, *status = 1 and no model is created.  objective_trace receives min(iters, trace_cap)
+ * values.  sum_diagL / sum_log_diagL are over the final factor of B = I + W^1/2 K W^1/2 (A.3).
+ * status: 0 converged, 1 guard fired ("Apparently does not converge."), 2 not positive definite. */
+int gprc_gpc_fit(gprc_ctx* ctx, const gprc_kernel* k, const double* X, int d, long n, const double* y, double eps,
+                 int guard, int max_iter, gprc_gpc** out, int* iters, double* objective_trace, int trace_cap,
+                 double* sum_diagL, double* sum_log_diagL, int* status);
+int gprc_gpc_fit_precomputed(gprc_ctx* ctx, const double* K, long n, const double* y, double eps, int guard,
+                             int max_iter, gprc_gpc** out, int* iters, double* objective_trace, int trace_cap,
+                             double* sum_diagL, double* sum_log_diagL, int* status);
+/* fs_bar and Vfs of GPC$predict_class, R/GPCclass.R:110-115 (the quadrature of :116-117 stays on the host). */
+int gprc_gpc_predict_latent(gprc_gpc* g, const double* Xs, long m, double* fs_bar, double* Vfs);
+int gprc_gpc_predict_latent_precomputed(gprc_gpc* g, const double* Ks, const double* kss, long m, double* fs_bar,
+                                        double* Vfs);
+int gprc_gpc_get(gprc_gpc* g, int what, double* host);
+long gprc_gpc_n(const gprc_gpc* g);
+void gprc_gpc_free(gprc_gpc* g);
+
+/* ---- raw device primitives (tests, roofline microbenchmarks) ---------------------------------------------- */
+/* In-place blocked Cholesky of the lower triangle of the n x n column-major device matrix dA (ld >= n, both
+ * multiples of 128).  dinv: device workspace (n/128) * 128*128 doubles receiving the inverted diagonal blocks. */
+int gprc_dev_potrf(gprc_ctx* ctx, double* dA, long n, long ld, double* dinv, long* info);
+/* C (M x N) = beta*C + alpha * A (M x K, col-major) * op(B); transb = 1: B is N x K col-major (C += A B^T),
+ * transb = 0: B is K x N col-major.  M, N multiples of 128, K multiple of 16. */
+int gprc_dev_dgemm(gprc_ctx* ctx, int transb, long M, long N, long K, double alpha, const double* dA, long lda,
+                   const double* dB, long ldb, double beta, double* dC, long ldc);
+/* W = L^-1 for a lower-triangular n x n device matrix whose diagonal blocks' inverses are in dinv. dscratch: n x n. */
+int gprc_dev_trtri(gprc_ctx* ctx, const double* dL, long n, long ld, const double* dinv, double* dW,
+                   double* dscratch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPRC_H */

@@ -1,0 +1,648 @@
+"""CPU oracle: a NumPy/SciPy restatement of the reference's GP hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this module; only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may.
+
+The reference (MoHawastaken/Gaussian-Process-Regression, R package ``gprc``) is pure R and delegates all numerics to
+base R (``chol`` = LAPACK dpotrf, ``solve`` = dgesv, ``%*%`` = BLAS, ``det`` = dgetrf, ``stats::optim`` = Brent fmin /
+vmmin BFGS, ``stats::integrate`` = QUADPACK dqagi).  R is not installed in this image, so the reference cannot be
+executed; this file restates its arithmetic line by line with the same LAPACK/QUADPACK algorithms from SciPy
+(OpenBLAS).  R's optimisers are restated from R's C sources (src/appl/fmin.c ``Brent_fmin``, src/appl/optim.c
+``vmmin``; base R is an unpinned third-party dependency of the reference, DESCRIPTION:1-32).
+
+Pinning: the only numeric known answers the reference holds are the four closed-form predictions of
+tests/testthat/test-gpr.R:5-28; they, the eight GPC inequalities of tests/testthat/test-gpc.R (argument order fixed,
+SURVEY.md section 4) and the six model-selection outcomes of tests/testthat/test-fit.R are checked in
+tests/test_oracle.py.  Everything else (logp, alpha, L, logq, f_hat, gradients, n > 25) is PARITY UNPINNED by the
+reference and pinned only by this restatement.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import numpy as np
+import scipy.integrate
+import scipy.linalg
+
+EPS = np.finfo(float).eps
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernels, R/GPRclass.R:381-403.  ``x`` and ``y`` are D x N arrays (columns are points) -> length-N vector
+# (the ``.matrix`` methods), or 1-D vectors -> scalar (the ``.numeric`` methods).
+# ---------------------------------------------------------------------------------------------------------------
+def _r_pow(x, p):
+    """R's ``^``: exponent exactly 2 is x*x, everything else libm pow (arithmetic.c R_POW)."""
+    if np.isscalar(p) and p == 2.0:
+        return x * x
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        return np.power(x, p)
+
+
+def _is_matrix(x):
+    return isinstance(x, np.ndarray) and x.ndim == 2
+
+
+def constant(x, y, c):  # R/GPRclass.R:381-383
+    return np.full(x.shape[1], float(c)) if _is_matrix(x) else float(c)
+
+
+def linear(x, y, sigma):  # R/GPRclass.R:385-387: colSums(sigma * x * y); sigma recycles down the rows
+    sigma = np.asarray(sigma, dtype=float)
+    if _is_matrix(x):
+        s = np.resize(sigma, x.shape[0])[:, None] if sigma.ndim else sigma
+        return np.sum(s * x * y, axis=0)
+    return float(np.sum(sigma * np.asarray(x, float) * np.asarray(y, float)))
+
+
+def polynomial(x, y, sigma, p):  # R/GPRclass.R:389-391
+    if _is_matrix(x):
+        return _r_pow(np.sum(x * y, axis=0) + sigma, p)
+    return float(_r_pow(np.dot(np.asarray(x, float), np.asarray(y, float)) + sigma, p))
+
+
+def sqrexp(x, y, l):  # R/GPRclass.R:393-395
+    if _is_matrix(x):
+        return np.exp(-np.sum(_r_pow(x - y, 2.0), axis=0) / (2 * l * l))
+    d = np.asarray(x, float) - np.asarray(y, float)
+    return float(np.exp(-np.sum(d * d) / (2 * l * l)))
+
+
+def gammaexp(x, y, l, gamma):  # R/GPRclass.R:397-399
+    if _is_matrix(x):
+        return np.exp(-_r_pow(np.sqrt(np.sum(_r_pow(x - y, 2.0), axis=0)) / l, gamma))
+    d = np.asarray(x, float) - np.asarray(y, float)
+    return float(np.exp(-_r_pow(np.sqrt(np.sum(d * d)) / l, gamma)))
+
+
+def rationalquadratic(x, y, l, alpha):  # R/GPRclass.R:401-403
+    if _is_matrix(x):
+        return _r_pow(1 + np.sum(_r_pow(x - y, 2.0), axis=0) / (2 * alpha * (l * l)), -alpha)
+    d = np.asarray(x, float) - np.asarray(y, float)
+    return float(_r_pow(1 + np.sum(d * d) / (2 * alpha * (l * l)), -alpha))
+
+
+def cov_func(func, **kwargs):  # R/GPRclass.R:424-427
+    return lambda x, y: func(x, y, **kwargs)
+
+
+def as_matrix(X):
+    """``if (!is.matrix(X)) dim(X) <- c(1, length(X))``, R/GPRclass.R:132, R/GPCclass.R:70."""
+    X = np.asarray(X, dtype=float)
+    if X.ndim < 2:
+        X = X.reshape(1, -1)
+    return X
+
+
+def covariance_matrix(A, B, k, chunk=1 << 22):
+    """R/GPRclass.R:355-357: outer(1:ncol(A), 1:ncol(B), function(i, j) k(A[, i], B[, j])).
+
+    ``outer`` calls ``k`` once on the gathered D x (nA nB) operands; gathering is done in column chunks here so that the
+    intermediate stays bounded (same values, same per-entry arithmetic)."""
+    A = as_matrix(A)
+    B = as_matrix(B)
+    nA, nB = A.shape[1], B.shape[1]
+    out = np.empty((nA, nB))
+    cols = max(1, chunk // max(nA * A.shape[0], 1))
+    for j0 in range(0, nB, cols):
+        j1 = min(nB, j0 + cols)
+        ii = np.tile(np.arange(nA), j1 - j0)
+        jj = np.repeat(np.arange(j0, j1), nA)
+        out[:, j0:j1] = np.asarray(k(A[:, ii], B[:, jj])).reshape(j1 - j0, nA).T
+    return out
+
+
+def _solve(A, b, literal):
+    """R's ``solve(A, b)`` is dgesv (LU) even for triangular A; generous = substitution."""
+    if literal:
+        return np.linalg.solve(A, b)
+    lower = np.allclose(A, np.tril(A))
+    return scipy.linalg.solve_triangular(A, b, lower=lower)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPR, R/GPRclass.R:116-170
+# ---------------------------------------------------------------------------------------------------------------
+class GPR:
+    def __init__(self, X, y, noise=0.0, k=None, literal=False):
+        X = as_matrix(X)  # :132
+        y = np.asarray(y, dtype=float)
+        assert y.ndim == 1 and len(y) == X.shape[1] and noise >= 0 and callable(k)  # :129-133
+        self.X, self.y, self.k, self.literal = X, y, k, literal
+        n = X.shape[1]
+        K = covariance_matrix(X, X, k)  # :138
+        new_noise = noise
+        L = None
+        self.noise_warning = None
+        for i in range(1, 11):  # :141-148
+            try:
+                L = scipy.linalg.cholesky(K + new_noise * np.eye(n), lower=True)  # t(chol(.))  :142
+            except np.linalg.LinAlgError:
+                L = None
+            if L is not None:
+                if i > 1:
+                    self.noise_warning = "Noise got changed to %s to avoid errors in cholesky decomposition" % new_noise
+                break
+            new_noise = 0.01 * i + noise
+        if L is None:  # :149
+            raise ValueError("Inputs lead to non positive definite covariance matrix. "
+                             "Try using a larger noise or a smaller lengthscale.")
+        self.L = L
+        self.noise = new_noise
+        self.alpha = _solve(L.T, _solve(L, y, literal), literal)  # :152
+        self.logp = -0.5 * (y @ self.alpha) - np.sum(np.log(np.diag(L))) - n / 2 * math.log(2 * math.pi)  # :153
+
+    def predict(self, X_star, pointwise_var=True):  # :155-170
+        X_star = np.asarray(X_star, dtype=float)
+        D = self.X.shape[0]
+        assert X_star.size % D == 0
+        if X_star.ndim < 2:
+            X_star = X_star.reshape(-1, D).T  # dim(X_star) <- c(D, length/D): column-major fill   :157-159
+        K_star = covariance_matrix(self.X, X_star, self.k)  # :160
+        mean = K_star.T @ self.alpha  # :161
+        v = _solve(self.L, K_star, self.literal)  # :162
+        if pointwise_var:
+            var = self.k(X_star, X_star) - np.sum(v * v, axis=0)  # :164
+            return np.column_stack([mean, var])  # :165
+        cov = covariance_matrix(X_star, X_star, self.k) - v.T @ v  # :167
+        return mean.reshape(-1, 1), cov
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPC, R/GPCclass.R:55-118
+# ---------------------------------------------------------------------------------------------------------------
+def sigmoid(x):  # R/GPCclass.R:63
+    with np.errstate(over="ignore"):
+        return 1 / (1 + np.exp(-x))
+
+
+class ConvergenceError(RuntimeError):
+    pass
+
+
+class GPC:
+    def __init__(self, X, y, k, epsilon=1e-5, literal=False, guard=True, max_iter=10000):
+        X = as_matrix(X)
+        y = np.asarray(y, dtype=float)
+        assert y.ndim == 1 and len(y) == X.shape[1] and epsilon > 0 and callable(k)  # :67-71
+        n = len(y)
+        K = covariance_matrix(X, X, k)  # :73
+        f = np.zeros(n)  # :74
+        it = 0
+        trace = []
+        while True:  # :76-97
+            it += 1
+            P = sigmoid(f)
+            W = (1 - P) * P
+            sw = np.sqrt(W)
+            L = scipy.linalg.cholesky(np.eye(n) + np.outer(sw, sw) * K, lower=True)  # :80
+            b = W * f + (y + 1) / 2 - P  # :81
+            inter = _solve(L, sw * (K @ b), literal)  # :82
+            inter = _solve(L.T, inter, literal)  # :83
+            a = b - sw * inter  # :84
+            f = K @ a  # :85
+            with np.errstate(over="ignore"):
+                objective = -np.sum(a * f) / 2 - np.sum(np.log(1 + np.exp(-y * f)))  # :86
+            trace.append(objective)
+            if it > 1:
+                if abs(objective - last_objective) < epsilon:  # :88
+                    break
+                elif guard and least_objective + 10 < objective:  # :90  (mis-signed guard)
+                    raise ConvergenceError("Apparently does not converge.")
+            else:
+                least_objective = objective
+            last_objective = objective
+            if it >= max_iter:
+                break
+        self.iterations = it
+        self.objective_trace = trace
+        P = sigmoid(f)  # :99-100
+        W = (1 - P) * P
+        self.f_hat = f
+        self.L = scipy.linalg.cholesky(np.eye(n) + np.outer(np.sqrt(W), np.sqrt(W)) * K, lower=True)  # :102
+        self.logq = objective - np.sum(np.diag(self.L))  # :103  (sum of the diagonal, not its log: A.3)
+        self.sum_log_diagL = float(np.sum(np.log(np.diag(self.L))))
+        self.X, self.y, self.k, self.literal = X, y, k, literal
+
+    def predict_latent(self, X_star):  # :109-115
+        X_star = np.asarray(X_star, dtype=float)
+        if X_star.ndim < 2:
+            X_star = X_star.reshape(1, -1)  # :109 (always one row)
+        P = sigmoid(self.f_hat)
+        W = P * (1 - P)
+        K_star = covariance_matrix(self.X, X_star, self.k)
+        fs_bar = K_star.T @ ((self.y + 1) / 2 - P)
+        v = _solve(self.L, np.sqrt(W)[:, None] * K_star, self.literal)
+        Vfs = self.k(X_star, X_star) - np.sum(v * v, axis=0)
+        return fs_bar, Vfs
+
+    def predict_class(self, X_star):  # :108-118
+        fs_bar, Vfs = self.predict_latent(X_star)
+        return np.array([logistic_gaussian_integral(m, s) for m, s in zip(fs_bar, Vfs)])
+
+
+def logistic_gaussian_integral(mean, sd):
+    """integrate(function(z) sigmoid(z) * dnorm(z, mean, sd = Vfs[i]), -Inf, Inf)$value, R/GPCclass.R:116-117.
+
+    NB the reference passes the latent *variance* as ``sd``.  R's integrate = QUADPACK dqagi with
+    rel.tol = abs.tol = .Machine$double.eps^0.25 and 100 subdivisions; scipy.integrate.quad over an infinite range is
+    the same routine."""
+    tol = EPS ** 0.25
+
+    def integrand(z):
+        return sigmoid(z) * math.exp(-0.5 * ((z - mean) / sd) ** 2) / (sd * math.sqrt(2 * math.pi))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        val, _err, info, *rest = scipy.integrate.quad(integrand, -np.inf, np.inf, epsabs=tol, epsrel=tol, limit=100,
+                                                      full_output=1)
+    return val
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fit(), R/fit.R
+# ---------------------------------------------------------------------------------------------------------------
+def _deriv_sqrexp(x, y, l):  # R/fit.R:4-7
+    r = math.sqrt(np.sum((x - y) ** 2))
+    return np.array([r ** 2 / l ** 3 * math.exp(-r ** 2 / (l ** 2 * 2))])
+
+
+def _deriv_gammaexp(x, y, gamma, l):  # R/fit.R:10-13  (argument order (gamma, l): SURVEY.md A.6)
+    r = math.sqrt(np.sum((x - y) ** 2))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rl = np.float64(r / l)
+        e = np.exp(-rl ** gamma)
+        return np.array([-e * rl ** gamma * np.log(rl), e * gamma * np.float64(r) ** gamma / (l ** (gamma + 1))])
+
+
+def _deriv_polynomial(x, y, sigma, p):  # R/fit.R:20-22
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.float64(np.dot(x, y) + sigma)
+        return np.array([p * s ** (p - 1), s ** p * np.log(s)])
+
+
+def _deriv_rationalquadratic(x, y, alpha, l):  # R/fit.R:25-31 (argument order (alpha, l): A.6)
+    r = np.sum((x - y) ** 2)
+    base = r / (2 * l ** 2 * alpha) + 1
+    return np.array([
+        (base ** (-alpha) * (r - (2 * l ** 2 * alpha + r) * math.log(base))) / (2 * l ** 2 * alpha + r),
+        (r * base ** (-alpha - 1)) / (l ** 3),
+    ])
+
+
+cov_dict = {  # R/fit.R:2-33, insertion order = names(cov_dict)
+    "sqrexp": dict(func=sqrexp, deriv=_deriv_sqrexp, start=[1.0]),
+    "gammaexp": dict(func=gammaexp, deriv=_deriv_gammaexp, start=[1.0, 1.0]),
+    "constant": dict(func=constant, deriv=lambda x, y, c: np.array([0.0]), start=[1.0]),
+    "linear": dict(func=linear, deriv=lambda x, y, sigma: np.array([sigma]), start=[1.0]),
+    "polynomial": dict(func=polynomial, deriv=_deriv_polynomial, start=[1.0, 2.0]),
+    "rationalquadratic": dict(func=rationalquadratic, deriv=_deriv_rationalquadratic, start=[1.0, 1.0]),
+}
+
+
+class OptimError(RuntimeError):
+    pass
+
+
+def dens(X, y, noise, name, v, minors="literal"):
+    """log p(y | X, theta), R/fit.R:117-124.  ``v`` is passed positionally to the kernel (R/fit.R:118).
+
+    minors = "literal": the positive-definiteness pre-check of R/fit.R:119 via det() of every leading minor
+    (det = exp(log-modulus) underflows to 0 when the log determinant drops below about -745: SURVEY.md A.4);
+    "cholesky": the same check in exact arithmetic (Cholesky succeeds); raises OptimError when the check fails."""
+    X = as_matrix(X)
+    n = X.shape[1]
+    func = cov_dict[name]["func"]
+    K = covariance_matrix(X, X, lambda a, b: func(a, b, *v))
+    Kn = K + noise * np.eye(n)
+    if minors == "literal":
+        dets = []
+        for i in range(1, n + 1):
+            sign, logdet = np.linalg.slogdet(Kn[:i, :i])  # det() = LU, exp of the log-modulus
+            dets.append(sign * math.exp(logdet) if np.isfinite(logdet) else 0.0)
+        if not (min(dets) > 0):
+            raise OptimError("min(sapply(... det ...)) > 0 is not TRUE")
+    try:
+        L = scipy.linalg.cholesky(Kn, lower=True)
+    except np.linalg.LinAlgError as e:
+        raise OptimError(str(e))
+    if not np.all(np.isfinite(L)):
+        raise OptimError("non-finite factor")
+    alpha = scipy.linalg.solve_triangular(L.T, scipy.linalg.solve_triangular(L, y, lower=True), lower=False)
+    return float(-0.5 * (y @ alpha) - np.sum(np.log(np.diag(L))) - n / 2 * math.log(2 * math.pi))
+
+
+def dens_deriv(X, y, noise, name, v):
+    """Gradient exactly as coded in R/fit.R:126-139: noise-free K, explicit inverse by LU,
+    0.5 * sum(diag(alpha alpha' - K^-1) %*% dK_i), derivative called with ``v`` in positional order."""
+    X = as_matrix(X)
+    n = X.shape[1]
+    func, deriv = cov_dict[name]["func"], cov_dict[name]["deriv"]
+    nparam = len(cov_dict[name]["start"])
+    K = np.zeros((n, n))
+    Kd = np.zeros((n, n, nparam))
+    for i in range(n):
+        for j in range(n):
+            K[i, j] = func(X[:, i], X[:, j], *v)
+            Kd[i, j, :] = deriv(X[:, i], X[:, j], *v)
+    # solve(K): dgesv with R's reciprocal-condition guard (rcond < .Machine$double.eps -> error)
+    if not np.all(np.isfinite(K)) or 1.0 / np.linalg.cond(K, 1) < EPS:
+        raise OptimError("system is computationally singular")
+    K_inv = np.linalg.inv(K)
+    alpha = K_inv @ y
+    dvec = alpha * alpha - np.diag(K_inv)
+    return np.array([0.5 * np.sum(dvec @ Kd[:, :, i]) for i in range(nparam)])
+
+
+# ---- R's optimisers ------------------------------------------------------------------------------------------
+def brent_fmin(f, ax, bx, tol):
+    """R src/appl/fmin.c Brent_fmin (the engine of optimize() and optim(method = "Brent"))."""
+    c = (3.0 - math.sqrt(5.0)) * 0.5
+    eps = math.sqrt(EPS)
+    a, b = ax, bx
+    v = a + c * (b - a)
+    w = x = v
+    d = e = 0.0
+    fx = f(x)
+    fv = fw = fx
+    tol3 = tol / 3.0
+    while True:
+        xm = (a + b) * 0.5
+        tol1 = eps * abs(x) + tol3
+        t2 = tol1 * 2.0
+        if abs(x - xm) <= t2 - (b - a) * 0.5:
+            break
+        p = q = r = 0.0
+        if abs(e) > tol1:
+            r = (x - w) * (fx - fv)
+            q = (x - v) * (fx - fw)
+            p = (x - v) * q - (x - w) * r
+            q = (q - r) * 2.0
+            if q > 0.0:
+                p = -p
+            else:
+                q = -q
+            r = e
+            e = d
+        if abs(p) >= abs(q * 0.5 * r) or p <= q * (a - x) or p >= q * (b - x):
+            e = (b - x) if x < xm else (a - x)
+            d = c * e
+        else:
+            d = p / q
+            u = x + d
+            if u - a < t2 or b - u < t2:
+                d = tol1
+                if x >= xm:
+                    d = -d
+        if abs(d) >= tol1:
+            u = x + d
+        elif d > 0.0:
+            u = x + tol1
+        else:
+            u = x - tol1
+        fu = f(u)
+        if fu <= fx:
+            if u < x:
+                b = x
+            else:
+                a = x
+            v, w, x = w, x, u
+            fv, fw, fx = fw, fx, fu
+        else:
+            if u < x:
+                a = u
+            else:
+                b = u
+            if fu <= fw or w == x:
+                v, fv, w, fw = w, fw, u, fu
+            elif fu <= fv or v == x or v == w:
+                v, fv = u, fu
+    return x
+
+
+def vmmin(b0, fminfn, fmingr, maxit=100, abstol=-math.inf, reltol=math.sqrt(EPS)):
+    """R src/appl/optim.c vmmin (optim(method = "BFGS")).  Returns (par, value, fail)."""
+    stepredn, acctol, reltest = 0.2, 0.0001, 10.0
+    b = np.array(b0, dtype=float)
+    n = len(b)
+    B = np.zeros((n, n))
+    f = fminfn(b)
+    if not math.isfinite(f):
+        raise OptimError("initial value in 'vmmin' is not finite")
+    Fmin = f
+    funcount = gradcount = 1
+    g = np.array(fmingr(b), dtype=float)
+    it = 1
+    ilast = gradcount
+    t = np.zeros(n)
+    X = np.zeros(n)
+    c = np.zeros(n)
+    while True:
+        if ilast == gradcount:
+            B[:] = 0.0
+            for i in range(n):
+                B[i, i] = 1.0
+        X[:] = b
+        c[:] = g
+        gradproj = 0.0
+        for i in range(n):
+            s = 0.0
+            for j in range(i + 1):
+                s -= B[i, j] * g[j]
+            for j in range(i + 1, n):
+                s -= B[j, i] * g[j]
+            t[i] = s
+            gradproj += s * g[i]
+        if gradproj < 0.0:
+            steplength = 1.0
+            accpoint = False
+            while True:
+                count = 0
+                for i in range(n):
+                    b[i] = X[i] + steplength * t[i]
+                    if reltest + X[i] == reltest + b[i]:
+                        count += 1
+                if count < n:
+                    f = fminfn(b)
+                    funcount += 1
+                    accpoint = math.isfinite(f) and (f <= Fmin + gradproj * steplength * acctol)
+                    if not accpoint:
+                        steplength *= stepredn
+                if count == n or accpoint:
+                    break
+            enough = (f > abstol) and abs(f - Fmin) > reltol * (abs(Fmin) + reltol)
+            if not enough:
+                count = n
+                Fmin = f
+            if count < n:
+                Fmin = f
+                g = np.array(fmingr(b), dtype=float)
+                gradcount += 1
+                it += 1
+                D1 = 0.0
+                for i in range(n):
+                    t[i] = steplength * t[i]
+                    c[i] = g[i] - c[i]
+                    D1 += t[i] * c[i]
+                if D1 > 0:
+                    D2 = 0.0
+                    for i in range(n):
+                        s = 0.0
+                        for j in range(i + 1):
+                            s += B[i, j] * c[j]
+                        for j in range(i + 1, n):
+                            s += B[j, i] * c[j]
+                        X[i] = s
+                        D2 += s * c[i]
+                    D2 = 1.0 + D2 / D1
+                    for i in range(n):
+                        for j in range(i + 1):
+                            B[i, j] += (D2 * t[i] * t[j] - X[i] * c[j] - t[i] * X[j]) / D1
+                else:
+                    ilast = gradcount
+            else:
+                if ilast < gradcount:
+                    count = 0
+                    ilast = gradcount
+        else:
+            count = 0
+            if ilast == gradcount:
+                count = n
+            else:
+                ilast = gradcount
+        if it >= maxit:
+            break
+        if gradcount - ilast > 2 * n:
+            ilast = gradcount
+        if not (count != n or ilast != gradcount):
+            break
+    return b, Fmin, (0 if it < maxit else 1)
+
+
+def r_optim(start, fn, gr=None, method="BFGS", lower=None, upper=None, fnscale=-1.0):
+    """stats::optim for the two methods fit() uses, with control = list(fnscale = -1) (R/fit.R:149-150,158)."""
+    if method == "Brent":
+        x = brent_fmin(lambda p: fn(np.array([p])) / fnscale, lower, upper, math.sqrt(EPS))
+        return dict(par=np.array([x]), value=fn(np.array([x])))
+    assert gr is not None
+    par, val, _fail = vmmin(np.asarray(start, float), lambda p: fn(p) / fnscale,
+                            lambda p: np.asarray(gr(p), float) / fnscale)
+    return dict(par=par, value=val * fnscale)
+
+
+def optim_until_error(start, f, **kw):
+    """R/fit.R:47-69: objective errors become -10000; if optim() itself throws, the best recorded evaluation wins."""
+    record = []
+
+    def f_new(p):
+        try:
+            out = f(p)
+        except (OptimError, np.linalg.LinAlgError, FloatingPointError, ValueError, ZeroDivisionError):
+            return -10000.0
+        if not out == -10000:
+            record.append((np.array(p, dtype=float), out))
+        return out
+
+    gr = kw.pop("gr", None)
+    try:
+        return r_optim(start, f_new, gr=gr, **kw)
+    except (OptimError, np.linalg.LinAlgError, FloatingPointError, ValueError, ZeroDivisionError):
+        if not record:
+            try:
+                value = f(np.asarray(start, float))
+            except Exception:
+                value = -10000.0
+            return dict(par=np.asarray(start, float), value=value)
+        best = int(np.argmax([r[1] for r in record]))
+        return dict(par=record[best][0], value=record[best][1])
+
+
+def fit(X, y, noise, cov_names=None, minors="literal"):
+    """R/fit.R:110-169."""
+    X = as_matrix(X)
+    y = np.asarray(y, float)
+    cov_names = list(cov_dict) if cov_names is None else list(cov_names)
+    params, score = [], []
+    for cov in cov_names:  # :113
+        nparam = len(cov_dict[cov]["start"])
+        f = lambda v, cov=cov: dens(X, y, noise, cov, list(np.atleast_1d(v)), minors=minors)
+        kw = {}
+        if cov in ("sqrexp", "gammaexp", "rationalquadratic", "polynomial"):  # :125
+            kw["gr"] = lambda v, cov=cov: dens_deriv(X, y, noise, cov, list(np.atleast_1d(v)))
+        if nparam == 1:  # :143-144
+            kw.update(method="Brent", lower=0.0, upper=10.0)
+        else:
+            kw.update(method="BFGS")
+        if cov == "polynomial":  # :145-156
+            cands = []
+            for i in range(1, 11):
+                q = optim_until_error([cov_dict[cov]["start"][0]], lambda sig, i=i: f([float(np.atleast_1d(sig)[0]), float(i)]),
+                                      method="Brent", lower=0.0, upper=5.0)
+                cands.append(q)
+            best = int(np.argmax([q["value"] for q in cands]))
+            p = dict(par=np.array([float(cands[best]["par"][0]), float(best + 1)]), value=cands[best]["value"])
+        else:
+            p = optim_until_error(cov_dict[cov]["start"], f, **kw)
+        params.append(np.atleast_1d(p["par"]))
+        score.append(float(p["value"]))
+    best = int(np.argmax(score))  # :164-165
+    name, par = cov_names[best], params[best]
+    func = cov_dict[name]["func"]
+    return dict(par=par, cov=name, score=score, func=lambda x, y_: func(x, y_, *par))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload generators (R/simulation.R) used by tests and bench
+# ---------------------------------------------------------------------------------------------------------------
+def combine_all(lst):
+    """R/simulation.R:338-349: all combinations of the per-dimension grids, D x prod(lengths)."""
+    l = len(lst)
+    lengths = [len(v) for v in lst]
+    prods = np.concatenate([[1], np.cumprod(lengths)])
+    rev_prods = np.concatenate([[1], np.cumprod(lengths[::-1])])
+    out = np.zeros((l, int(prods[l])))
+    for k in range(1, l + 1):
+        out[k - 1, :] = np.tile(np.repeat(np.asarray(lst[k - 1], float), int(rev_prods[l - k])), int(prods[k - 1]))
+    return out
+
+
+def make_config(cfg, seed=None, n=None, m=None):
+    """Synthetic inputs of the BASELINE.json configs; NumPy default_rng so that every
+    implementation sees identical bits."""
+    if cfg == "C1":  # simulate_regression 1-D, R/simulation.R:91,101-102,393
+        rng = np.random.default_rng(1 if seed is None else seed)
+        n = 200 if n is None else n
+        m = 1000 if m is None else m
+        X = rng.uniform(-6, 6, size=(1, n))
+        y = 0.1 * X[0] ** 3 + rng.normal(0, 0.1, n)
+        Xs = np.linspace(-6, 6, m).reshape(1, m)
+        return dict(X=X, y=y, Xs=Xs, noise=0.01, kernel=("sqrexp", dict(l=1.0)))
+    if cfg == "C2":  # simulate_classification 2-D, R/simulation.R:319-329,434
+        rng = np.random.default_rng(2 if seed is None else seed)
+        n = 2000 if n is None else n
+        m = 10000 if m is None else m
+        X = rng.uniform(-4, 4, size=(2, n))
+        y = np.where(np.sum(np.abs(X), axis=0) > 2.5, 1.0, -1.0)
+        side = int(math.ceil(round(m ** 0.5, 9)))
+        s = np.linspace(-4, 4, side)
+        Xs = combine_all([s, s])
+        return dict(X=X, y=y, Xs=Xs, eps=1e-5, kernel=("sqrexp", dict(l=0.2)))
+    if cfg == "C3":
+        rng = np.random.default_rng(3 if seed is None else seed)
+        n = 5000 if n is None else n
+        X = rng.uniform(-2, 2, size=(4, n))
+        y = np.sum(np.sin(X), axis=0) + rng.normal(0, 0.1, n)
+        starts = np.vstack([[1.0, 1.0], np.exp(rng.uniform(np.log(0.1), np.log(10), size=(15, 2)))])
+        return dict(X=X, y=y, noise=0.05, kernel_name="rationalquadratic", starts=starts)
+    if cfg in ("C4", "C5"):
+        rng = np.random.default_rng((4 if cfg == "C4" else 5) if seed is None else seed)
+        n = (50000 if cfg == "C4" else 200000) if n is None else n
+        m = 1000000 if m is None else m
+        X = rng.uniform(-1, 1, size=(8, n))
+        y = np.sum(np.sin(math.pi * X), axis=0) + rng.normal(0, 0.1, n)
+        Xs = rng.uniform(-1, 1, size=(8, m)) if cfg == "C4" else None
+        return dict(X=X, y=y, Xs=Xs, noise=0.01 if cfg == "C4" else 0.1, kernel=("sqrexp", dict(l=1.0)))
+    raise ValueError(cfg)

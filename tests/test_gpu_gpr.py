@@ -1,0 +1,166 @@
+"""GPR parity: the reference's known-answer tests (tests/testthat/test-gpr.R) verbatim, then randomised differential
+tests against the oracle at the north_star tolerances: relative 1e-9 on predictive mean/variance, 1e-8 on logp."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MEAN_RTOL = 1e-9
+LOGP_RTOL = 1e-8
+
+
+def assert_mean_var(got, ref, kss):
+    """|d mean| <= 1e-9 max(|mean|, scale); |d var| <= 1e-9 max(|var|, k(x*, x*)) (cancellation-limited,
+    BASELINE.md section 3)."""
+    scale = np.maximum(np.abs(ref[:, 0]), np.max(np.abs(ref[:, 0])))
+    assert np.all(np.abs(got[:, 0] - ref[:, 0]) <= MEAN_RTOL * scale)
+    assert np.all(np.abs(got[:, 1] - ref[:, 1]) <= MEAN_RTOL * np.maximum(np.abs(ref[:, 1]), kss))
+
+
+def test_known_answers_test_gpr_R(gprc):
+    # tests/testthat/test-gpr.R:6-9
+    g1 = gprc.GPR.polynomial.new(np.array([[-0.5, 0.5]]), np.array([4.0, 4.0]), 0.5, 0.25, 1)
+    np.testing.assert_allclose(g1.predict(0.0), [[2.0, 1 / 8]], rtol=0, atol=1.5e-8)
+    # :12-15
+    g2 = gprc.GPR.constant.new(np.array([[1.0, 2.0]]), np.array([1.0, 3.0]), 1, 1)
+    np.testing.assert_allclose(g2.predict(3.0), [[4 / 3, 1 / 3]], rtol=0, atol=1.5e-8)
+    # :16-19
+    g3 = gprc.GPR.constant.new(np.array([[100.0, 54.0]]), np.array([5.0, 0.0]), 1, 1)
+    np.testing.assert_allclose(g3.predict(math.pi), [[5 / 3, 1 / 3]], rtol=0, atol=1.5e-8)
+    # :23-27
+    g4 = gprc.GPR.sqrexp.new(np.array([[1.0, 2.0]]), np.array([0.0, 1.0]), 1, 1)
+    e = math.exp
+    cov = 1 - (2 * e(-1) - 2 * e(-3) + 2 * e(-4)) / (4 - e(-1))
+    np.testing.assert_allclose(g4.predict(0.0), [[(2 * e(-2) - e(-1)) / (4 - e(-1)), cov]], rtol=0, atol=1.5e-8)
+    # regression values of the restatement
+    for g, lp in ((g1, -17.8378770664), (g2, -4.72051654408), (g3, -10.7205165441), (g4, -2.75810665086)):
+        assert g.logp.shape == (1, 1)
+        assert abs(g.logp[0, 0] - lp) < 1e-9
+
+
+def test_read_only_bindings(gprc):
+    g = gprc.GPR.sqrexp.new(np.array([[1.0, 2.0]]), np.array([0.0, 1.0]), 1, 1)
+    for name in ("X", "k", "y", "noise", "L", "alpha", "logp"):
+        with pytest.raises(AttributeError, match=r"`\$%s` is read only" % name):
+            setattr(g, name, 1)
+
+
+CASES = [
+    ("sqrexp", dict(l=1.0), 1, 200, 1000, 0.01),        # BASELINE config 1 scale
+    ("sqrexp", dict(l=1.0), 8, 900, 700, 0.01),         # config 4's kernel at oracle-sized n
+    ("gammaexp", dict(l=1.0, gamma=1.5), 8, 515, 300, 0.1),
+    ("rationalquadratic", dict(l=1.0, alpha=1.0), 4, 640, 129, 0.05),
+    ("polynomial", dict(sigma=1.0, p=3.0), 8, 300, 257, 0.1),
+    ("linear", dict(sigma=0.7), 3, 129, 50, 0.5),
+    ("constant", dict(c=2.0), 2, 64, 10, 1.0),
+]
+
+
+@pytest.mark.parametrize("name,params,D,n,m,noise", CASES)
+def test_gpr_matches_oracle(gprc, oracle, name, params, D, n, m, noise):
+    rng = np.random.default_rng(n + m)
+    lim = 6.0 if D == 1 else 1.0
+    X = rng.uniform(-lim, lim, (D, n))
+    y = np.sum(np.sin(X), axis=0) + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-lim, lim, (D, m))
+    Xs[:, 0] = X[:, 0]  # a test point on a training point: var << k**
+    g = gprc.GPR(X, y, noise, gprc.cov_func(getattr(gprc, name), **params))
+    o = oracle.GPR(X, y, noise, oracle.cov_func(getattr(oracle, name), **params))
+    assert g.noise == o.noise
+    assert abs(g.logp[0, 0] - o.logp) <= LOGP_RTOL * abs(o.logp)
+    got, ref = g.predict(Xs), o.predict(Xs)
+    assert got.shape == (m, 2)
+    kss = oracle.cov_func(getattr(oracle, name), **params)(Xs, Xs)
+    assert_mean_var(got, ref, kss)
+    # unpinned by the reference, pinned by the restatement: the factor and alpha
+    np.testing.assert_allclose(g.L, o.L, rtol=0, atol=1e-10 * np.max(np.abs(o.L)))
+    assert np.all(np.triu(g.L, 1) == 0)
+    np.testing.assert_allclose(g.alpha, o.alpha, rtol=0, atol=1e-8 * np.max(np.abs(o.alpha)))
+
+
+def test_predict_vector_reshape_rule(gprc, oracle):
+    # a bare vector is D x (length / D), column-major (R/GPRclass.R:157-159)
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-1, 1, (2, 50))
+    y = np.sin(X[0]) + X[1]
+    g = gprc.GPR(X, y, 0.1, gprc.cov_func(gprc.sqrexp, l=1.0))
+    o = oracle.GPR(X, y, 0.1, oracle.cov_func(oracle.sqrexp, l=1.0))
+    flat = rng.uniform(-1, 1, 14)
+    np.testing.assert_allclose(g.predict(flat), o.predict(flat), rtol=1e-9, atol=1e-12)
+    with pytest.raises(ValueError):
+        g.predict(np.zeros(3))
+
+
+def test_predict_full_covariance(gprc, oracle):
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-5, 5, (1, 150))
+    y = 0.1 * X[0] ** 3 + rng.normal(0, 0.1, 150)
+    Xs = np.linspace(-6, 6, 203)
+    g = gprc.GPR(X, y, 0.1, gprc.cov_func(gprc.sqrexp, l=1.0))
+    o = oracle.GPR(X, y, 0.1, oracle.cov_func(oracle.sqrexp, l=1.0))
+    mean, cov = g.predict(Xs, pointwise_var=False)
+    omean, ocov = o.predict(Xs, pointwise_var=False)
+    assert mean.shape == (203, 1) and cov.shape == (203, 203)
+    np.testing.assert_allclose(mean, omean, rtol=0, atol=1e-9 * np.max(np.abs(omean)))
+    np.testing.assert_allclose(cov, ocov, rtol=0, atol=1e-9)
+
+
+def test_noise_bump_schedule(gprc, oracle):
+    # duplicated points with zero noise: chol() fails, the constructor retries with noise + 0.01 i (R/GPRclass.R:141-148)
+    X = np.array([[0.0, 0.0, 1.0, 1.0, 2.0]])
+    y = np.array([1.0, 1.0, 2.0, 2.0, 0.5])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        g = gprc.GPR(X, y, 0.0, gprc.cov_func(gprc.sqrexp, l=1.0))
+    o = oracle.GPR(X, y, 0.0, oracle.cov_func(oracle.sqrexp, l=1.0))
+    assert g.noise == o.noise == 0.01
+    assert any("Noise got changed to 0.01" in str(x.message) for x in w)
+    np.testing.assert_allclose(g.predict(np.array([0.5])), o.predict(np.array([0.5])), rtol=1e-7)
+
+
+def test_not_positive_definite_raises(gprc):
+    # a negative "kernel": no noise of the schedule rescues it (R/GPRclass.R:149)
+    bad = lambda x, y: -5.0 * np.ones(x.shape[1])
+    with pytest.raises(ValueError, match="non positive definite"):
+        gprc.GPR(np.array([[0.0, 1.0, 2.0]]), np.array([1.0, 2.0, 3.0]), 0.0, bad)
+
+
+def test_closure_kernel_precomputed_path(gprc, oracle):
+    kappa = lambda x, y: np.exp(-3 * np.sum((x - y) ** 2, axis=0))
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-1, 1, (2, 140))
+    y = rng.standard_normal(140)
+    Xs = rng.uniform(-1, 1, (2, 77))
+    g = gprc.GPR(X, y, 0.2, kappa)
+    o = oracle.GPR(X, y, 0.2, kappa)
+    assert abs(g.logp[0, 0] - o.logp) <= LOGP_RTOL * abs(o.logp)
+    assert_mean_var(g.predict(Xs), o.predict(Xs), np.ones(77))
+
+
+def test_large_size_properties(gprc):
+    """Size-independent properties at a size the oracle cannot do in seconds (n = 8192, d = 8):
+    L L' reproduces K + noise I on sampled entries; alpha solves the system; var in [0, k**]."""
+    rng = np.random.default_rng(11)
+    n, D, m = 8192, 8, 4096
+    X = rng.uniform(-1, 1, (D, n))
+    y = np.sum(np.sin(np.pi * X), axis=0) + rng.normal(0, 0.1, n)
+    k = gprc.cov_func(gprc.sqrexp, l=1.0)
+    g = gprc.GPR(X, y, 0.01, k)
+    L = g.L
+    idx = rng.integers(0, n, 300)
+    jdx = rng.integers(0, n, 300)
+    Kij = np.array([gprc.sqrexp(X[:, i], X[:, j], 1.0) + (0.01 if i == j else 0.0) for i, j in zip(idx, jdx)])
+    LLt = np.einsum("ij,ij->i", L[idx, :], L[jdx, :])
+    assert np.max(np.abs(LLt - Kij)) < 1e-11
+    # residual of (K + noise I) alpha = y on sampled rows
+    Krows = gprc.covariance_matrix(X[:, idx[:50]], X, k).copy()
+    Krows[np.arange(50), idx[:50]] += 0.01
+    assert np.max(np.abs(Krows @ g.alpha - y[idx[:50]])) < 1e-8 * np.max(np.abs(g.alpha))
+    pred = g.predict(rng.uniform(-1, 1, (D, m)))
+    assert np.all(pred[:, 1] > -1e-9) and np.all(pred[:, 1] <= 1.0 + 1e-12)
+    # predicting at training points reproduces y up to the noise shrinkage: mean = y - noise * alpha
+    ptrain = g.predict(X[:, :256])
+    np.testing.assert_allclose(ptrain[:, 0], y[:256] - 0.01 * g.alpha[:256], rtol=0, atol=1e-8)

@@ -1,0 +1,121 @@
+"""Parity of the raw device primitives (DMMA GEMM core, blocked Cholesky, level-wise inversion, kernel-matrix build)
+against NumPy/SciPy and the oracle.  All through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(ctx, a):
+    return ctx.upload(np.asfortranarray(a))
+
+
+@pytest.mark.parametrize("transb", [1, 0])
+@pytest.mark.parametrize("shape", [(128, 128, 16), (256, 384, 528), (512, 128, 1024)])
+def test_dgemm(ctx, transb, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K + transb)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K)) if transb else rng.standard_normal((K, N))
+    Cm = rng.standard_normal((M, N))
+    dA, dB, dC = _dev(ctx, A), _dev(ctx, B), _dev(ctx, Cm)
+    ldb = N if transb else K
+    rc = ctx.lib.gprc_dev_dgemm(ctx.handle, transb, M, N, K, -1.5, dA, M, dB, ldb, 0.5, dC, M)
+    assert rc == 0, ctx.lib.gprc_last_error()
+    out = np.empty((M, N), order="F")
+    ctx.d2h(out, dC)
+    ref = 0.5 * Cm - 1.5 * (A @ (B.T if transb else B))
+    # same products, different summation order: a few ulp of the accumulated magnitude
+    assert np.max(np.abs(out - ref)) <= 1e-13 * np.sqrt(K) * 16
+    for p in (dA, dB, dC):
+        ctx.free(p)
+
+
+def _spd(n, seed):
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((n, n))
+    return G @ G.T / n + np.eye(n)
+
+
+@pytest.mark.parametrize("n", [128, 256, 640, 1152])
+def test_potrf_and_trtri(ctx, n):
+    A = _spd(n, n)
+    dA = _dev(ctx, A)
+    dinv = ctx.malloc(n * 128 * 8)
+    info = C.c_long(-1)
+    rc = ctx.lib.gprc_dev_potrf(ctx.handle, dA, n, n, dinv, C.byref(info))
+    assert rc == 0, ctx.lib.gprc_last_error()
+    assert info.value == 0
+    out = np.empty((n, n), order="F")
+    ctx.d2h(out, dA)
+    L = np.tril(out)
+    Lref = scipy.linalg.cholesky(A, lower=True)
+    assert np.max(np.abs(L - Lref)) <= 1e-12 * np.max(np.abs(Lref))
+    assert np.max(np.abs(L @ L.T - A)) <= 1e-13 * n
+    # inversion: W L = I
+    dW = ctx.malloc(n * n * 8)
+    rc = ctx.lib.gprc_dev_trtri(ctx.handle, dA, n, n, dinv, dW, dA)
+    assert rc == 0, ctx.lib.gprc_last_error()
+    W = np.empty((n, n), order="F")
+    ctx.d2h(W, dW)
+    W = np.tril(W)
+    assert np.max(np.abs(W @ L - np.eye(n))) <= 1e-11
+    for p in (dA, dinv, dW):
+        ctx.free(p)
+
+
+def test_potrf_reports_first_bad_pivot(ctx):
+    n = 384
+    A = _spd(n, 7)
+    A[200, 200] = -5.0  # leading minor 201 is the first that fails
+    dA = _dev(ctx, A)
+    dinv = ctx.malloc(n * 128 * 8)
+    info = C.c_long(-1)
+    assert ctx.lib.gprc_dev_potrf(ctx.handle, dA, n, n, dinv, C.byref(info)) == 0
+    assert info.value == 201
+    ctx.free(dA)
+    ctx.free(dinv)
+
+
+KERNELS = [
+    ("constant", dict(c=1.7)),
+    ("linear", dict(sigma=0.8)),
+    ("polynomial", dict(sigma=0.25, p=3.0)),
+    ("polynomial", dict(sigma=1.0, p=2.0)),
+    ("sqrexp", dict(l=0.7)),
+    ("gammaexp", dict(l=1.3, gamma=1.5)),
+    ("rationalquadratic", dict(l=0.9, alpha=2.5)),
+]
+
+
+@pytest.mark.parametrize("name,params", KERNELS)
+@pytest.mark.parametrize("D,nA,nB", [(1, 5, 3), (2, 70, 129), (8, 257, 64), (11, 33, 200)])
+def test_cov_matrix_matches_oracle(gprc, oracle, ctx, name, params, D, nA, nB):
+    rng = np.random.default_rng(D * 1000 + nA + nB)
+    A = rng.uniform(-1, 1, (D, nA))
+    B = rng.uniform(-1, 1, (D, nB))
+    B[:, 0] = A[:, 0]  # a coincident pair
+    got = gprc.covariance_matrix(A, B, gprc.cov_func(getattr(gprc, name), **params), ctx=ctx)
+    ref = oracle.covariance_matrix(A, B, oracle.cov_func(getattr(oracle, name), **params))
+    assert got.shape == (nA, nB)
+    # identical difference/sum order; exp/pow differ by <= 2 ulp between CUDA and glibc
+    np.testing.assert_allclose(got, ref, rtol=1e-14, atol=1e-300)
+
+
+def test_cov_matrix_linear_vector_sigma(gprc, oracle, ctx):
+    rng = np.random.default_rng(5)
+    A, B = rng.standard_normal((3, 40)), rng.standard_normal((3, 17))
+    sig = np.array([0.5, 2.0, 1.25])
+    got = gprc.covariance_matrix(A, B, gprc.cov_func(gprc.linear, sigma=sig), ctx=ctx)
+    ref = oracle.covariance_matrix(A, B, oracle.cov_func(oracle.linear, sigma=sig))
+    np.testing.assert_allclose(got, ref, rtol=1e-14)
+
+
+def test_cov_matrix_closure_goes_through_host(gprc, oracle):
+    # an opaque closure (test-gpc.R:7) is evaluated on the host exactly like the reference's outer()
+    kappa = lambda x, y: np.exp(-3 * (x - y) ** 2)[0]
+    X = np.arange(-1, 1.0001, 0.1).reshape(1, -1)
+    np.testing.assert_array_equal(gprc.covariance_matrix(X, X, kappa), oracle.covariance_matrix(X, X, kappa))
