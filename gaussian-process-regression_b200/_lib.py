@@ -180,7 +180,9 @@ class Context:
         check(self.lib.gprc_dev_d2h(self.handle, arr.ctypes.data_as(_P), p, arr.nbytes))
 
     def upload(self, arr: np.ndarray):
-        arr = np.ascontiguousarray(arr)
+        """Copy the array's buffer as it lies in memory (C- or Fortran-contiguous) to a new device buffer."""
+        if not (arr.flags.c_contiguous or arr.flags.f_contiguous):
+            arr = np.ascontiguousarray(arr)
         p = self.malloc(arr.nbytes)
         self.h2d(p, arr)
         return p
