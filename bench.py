@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline: "GPR train+predict sec at n=50k; Cholesky FP64 TFLOP/s vs peak; test pts/s".
+
+A step = one full pass of the hot path on BASELINE config 4: squared-exponential GPR,
+d = 8, n = 50 000 training points, noise 0.01 -> kernel-matrix build, Cholesky, alpha + logp, then predictive
+mean + variance of m = 1 000 000 test points.  With N GPUs the test points are split into N contiguous shards, one per
+rank, and every rank factorises its own replica (no data-path collective; total work fixed => "strong" scaling).
+
+  value   seconds per step with X, y, X_star already resident in HBM (device timed, max over ranks)
+  e2e     the same through the host API (GPR(X, y, noise, k); $predict(X_star)) with pinned HOST buffers: H2D of
+          X, y, X_star and D2H of mean/var inside the timed region
+  roofline      the dominant kernel (variance pass: V = L^-1 K_star, fused column norms) against the FP64 tensor
+                peak measured live with cuBLAS Dgemm (MEASURED_PEAKS.json has no FP64 figure)
+  cpu_baseline  the oracle (NumPy/SciPy/OpenBLAS restatement of the reference's R path) on the host cores, on a
+                bounded sample scaled by flop count to the full job (R is not installed: kind = "port")
+
+`--impl reference` times only that CPU path and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GPR train+predict sec at n=50k; Cholesky FP64 TFLOP/s vs peak; test pts/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--m", type=int, default=1000000)
+    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--cpu-sample-n", type=int, default=8192)
+    ap.add_argument("--cpu-sample-m", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_inputs(n, m, d):
+    """BASELINE config 4 generator (identical bits on every rank and in the CPU arm)."""
+    rng = np.random.default_rng(4)
+    X = rng.uniform(-1, 1, size=(d, n))
+    y = np.sum(np.sin(math.pi * X), axis=0) + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-1, 1, size=(d, m))
+    return X, y, Xs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle, bounded sample, scaled by algorithmic flops
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference(n, m, d, ns, ms, steps=1, warmup=0):
+    import scipy.linalg
+    from oracle import gprc_oracle as o
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    X, y, Xs = make_inputs(ns, ms, d)
+    k = o.cov_func(o.sqrexp, l=1.0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        K = o.covariance_matrix(X, X, k)                              # R/GPRclass.R:138
+        t1 = time.perf_counter()
+        L = scipy.linalg.cholesky(K + 0.01 * np.eye(ns), lower=True)  # :142
+        t2 = time.perf_counter()
+        alpha = scipy.linalg.solve_triangular(L.T, scipy.linalg.solve_triangular(L, y, lower=True), lower=False)
+        logp = -0.5 * (y @ alpha) - np.sum(np.log(np.diag(L))) - ns / 2 * math.log(2 * math.pi)
+        t3 = time.perf_counter()
+        Ks = o.covariance_matrix(X, Xs, k)                            # :160
+        mean = Ks.T @ alpha
+        t4 = time.perf_counter()
+        v = scipy.linalg.solve_triangular(L, Ks, lower=True)          # :162 ("generous": substitution, not dgesv)
+        var = k(Xs, Xs) - np.sum(v * v, axis=0)
+        t5 = time.perf_counter()
+        if it >= warmup:
+            times.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4))
+    tb, tc, ts, tk, tv = np.mean(np.array(times), axis=0)
+    # scale each phase by its algorithmic work
+    full = (tb * (n / ns) ** 2 + tc * (n / ns) ** 3 + ts * (n / ns) ** 2 + tk * (n * m) / (ns * ms)
+            + tv * (n * n * m) / (ns * ns * ms))
+    sample = ("oracle (NumPy/SciPy, OpenBLAS) on n=%d, m=%d of the same generator; phases build/chol/solve/Kstar/trsm "
+              "= %.2f/%.2f/%.2f/%.2f/%.2f s, each scaled by its algorithmic work to n=%d, m=%d (scaled, not run)"
+              % (ns, ms, tb, tc, ts, tk, tv, n, m))
+    return dict(value=full, unit="s", cores=threads, kind="port", sample=sample,
+                sample_seconds=float(tb + tc + ts + tk + tv),
+                chol_gflops=ns ** 3 / 3 / tc / 1e9, trsm_gflops=ns * ns * ms / tv / 1e9)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "500"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load: power above 40 % of the observed maximum
+        if pw:
+            thr = 0.4 * max(pw)
+            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        else:
+            load = sm
+        return dict(sm_mhz=float(np.median(load)) if load else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def fp64_tensor_peak_tflops(torch, dev):
+    """cuBLAS Dgemm 8192^3, best of 5 (burst) -- the denominator of the tensor roofline, measured in this run."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    torch.mm(a, b, out=c)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.mm(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, m, d = args.n, args.m, args.d
+    config = dict(workload="C4: GPR sqrexp(l=1)+iid noise 0.01, d=%d, n=%d train, m=%d test (mean+variance)" % (d, n, m),
+                  n=n, m=m, d=d, sharding="test points split across ranks, replicated factorisation",
+                  l2="inputs larger than L2 (L is %.1f GB)" % (8.0 * n * n / 1e9))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ref = cpu_reference(n, m, d, args.cpu_sample_n, args.cpu_sample_m, steps=max(1, args.steps),
+                            warmup=min(args.warmup, 1))
+        line = dict(metric=METRIC, value=ref["value"], unit="s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ref["value"] * 1e3, higher_is_better=False, scaling="strong", vs_baseline=None,
+                    dtype="f64", data="synthetic", config=config, impl="reference",
+                    cpu_baseline=dict(value=ref["value"], unit="s", cores=ref["cores"], kind=ref["kind"],
+                                      sample=ref["sample"]),
+                    e2e=dict(value=ref["value"], unit="s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    test_pts_per_s=m / ref["value"], cholesky_tflops=ref["chol_gflops"] / 1e3)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("GPRC_DEVICE", str(local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import gprc_b200 as g
+    ctx = g.Context(local)
+    lib = ctx.lib
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak_tf = fp64_tensor_peak_tflops(torch, dev)
+
+    X, y, Xs_all = make_inputs(n, m, d)
+    lo, hi = rank * m // world, (rank + 1) * m // world
+    m_local = hi - lo
+    xp = np.ascontiguousarray(X.T)                      # the ABI layout: points contiguous
+    xsp = np.ascontiguousarray(Xs_all[:, lo:hi].T)
+    del Xs_all
+    mean = np.empty(m_local)
+    var = np.empty(m_local)
+    for a in (xp, y, xsp, mean, var):                   # pinned host memory for the e2e leg
+        lib.gprc_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes)
+    dX, dy, dXs = ctx.upload(xp), ctx.upload(y), ctx.upload(xsp)
+    dmean, dvar = ctx.malloc(8 * m_local), ctx.malloc(8 * m_local)
+    spec = g.KernelSpec("sqrexp", l=1.0)
+    kc, _keep = spec.to_c()
+
+    def step_device():
+        h = C.c_void_p()
+        logp, info = C.c_double(0.0), C.c_long(0)
+        g._lib.check(lib.gprc_gpr_fit_dev(ctx.handle, kc, dX, d, n, dy, 0.01, C.byref(h), C.byref(logp), C.byref(info)))
+        assert info.value == 0, "not positive definite: %d" % info.value
+        g._lib.check(lib.gprc_gpr_predict_dev(h, dXs, m_local, dmean, dvar))
+        ctx.sync()
+        lib.gprc_gpr_free(h)
+        return logp.value
+
+    def step_host():
+        h = C.c_void_p()
+        logp, info = C.c_double(0.0), C.c_long(0)
+        g._lib.check(lib.gprc_gpr_fit(ctx.handle, kc, g._lib.dptr(xp), d, n, g._lib.dptr(y), 0.01, C.byref(h),
+                                      C.byref(logp), C.byref(info)))
+        assert info.value == 0
+        g._lib.check(lib.gprc_gpr_predict(h, g._lib.dptr(xsp), m_local, g._lib.dptr(mean), g._lib.dptr(var)))
+        lib.gprc_gpr_free(h)
+        return logp.value
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ctx.reset_timers()
+    ctx.mark(0)
+    t0 = time.perf_counter()
+    logp = 0.0
+    for _ in range(args.steps):
+        logp = step_device()
+    ctx.mark(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.elapsed_ms(0, 1)
+    timers, launches = ctx.timers()
+    clocks = sampler.stop() if rank == 0 else None
+    sec_per_step = max_over_ranks(dev_ms / 1e3 / args.steps)
+    wall_per_step = max_over_ranks(wall / args.steps)
+
+    # sanity of the result that was timed (finite, variance within [0, k**])
+    v = np.empty(min(m_local, 4096))
+    ctx.d2h(v, dvar)
+    assert np.all(np.isfinite(v)) and v.min() > -1e-8 and v.max() <= 1.0 + 1e-9, (v.min(), v.max())
+
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+        e2e = dict(value=e2e_s, unit="s", h2d_bytes_per_step=int(xp.nbytes + y.nbytes + xsp.nbytes) * world,
+                   d2h_bytes_per_step=int(mean.nbytes + var.nbytes) * world,
+                   note="host API gprc_gpr_fit + gprc_gpr_predict with pinned host buffers; bytes summed over ranks")
+
+    if rank == 0:
+        var_ms = timers["var"] / args.steps
+        flops_var = float(n) * n * m_local            # algorithmic: n^2 m  
+        achieved = flops_var / (var_ms * 1e-3) / 1e12 if var_ms > 0 else None
+        n_pad = (n + 127) // 128 * 128
+        chol_tf = n ** 3 / 3 / (timers["chol"] / args.steps * 1e-3) / 1e12
+        roofline = dict(kernel="gemm_kernel<TrmmNormPolicy> (variance pass v = L^-1 K_star, fused column norms)",
+                        bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
+                        frac=(achieved / peak_tf) if achieved else None, traffic=None,
+                        peak_source="cuBLAS Dgemm fp64 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json "
+                                    "holds no FP64 figure; of measured)",
+                        algorithmic_flops_per_step=flops_var, ms_per_step=var_ms,
+                        share_of_step=var_ms / (sec_per_step * 1e3))
+        line = dict(metric=METRIC, value=sec_per_step, unit="s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=sec_per_step * 1e3, higher_is_better=False, scaling="strong", vs_baseline=None,
+                    dtype="f64", data="synthetic", config=config, clocks=clocks, e2e=e2e,
+                    gpu_launches=int(launches), roofline=roofline,
+                    cholesky_tflops=chol_tf, cholesky_frac_of_peak=chol_tf / peak_tf,
+                    test_pts_per_s=m / sec_per_step, wall_s_per_step=wall_per_step, logp=logp,
+                    phase_ms_per_step={k: v / args.steps for k, v in timers.items() if v})
+        if not args.no_cpu_baseline and world == 1:
+            ref = cpu_reference(n, m, d, args.cpu_sample_n, args.cpu_sample_m)
+            line["cpu_baseline"] = dict(value=ref["value"], unit="s", cores=ref["cores"], kind=ref["kind"],
+                                        sample=ref["sample"])
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

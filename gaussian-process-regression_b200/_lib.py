@@ -43,6 +43,8 @@ SIGNATURES = {
     "gprc_ctx_sync": (C.c_int, [_P]),
     "gprc_ctx_reset_timers": (None, [_P]),
     "gprc_ctx_get_timers": (C.c_int, [_P, c_double_p, c_long_p]),
+    "gprc_ctx_mark": (C.c_int, [_P, C.c_int]),
+    "gprc_ctx_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, c_double_p]),
     "gprc_last_error": (C.c_char_p, []),
     "gprc_version": (C.c_int, []),
     "gprc_dev_malloc": (C.c_int, [_P, C.POINTER(_P), C.c_ulonglong]),
@@ -163,6 +165,14 @@ class Context:
         launches = C.c_long(0)
         check(self.lib.gprc_ctx_get_timers(self.handle, ms, C.byref(launches)))
         return {n: ms[i] for i, n in enumerate(T_NAMES)}, launches.value
+
+    def mark(self, slot):
+        check(self.lib.gprc_ctx_mark(self.handle, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_double(0.0)
+        check(self.lib.gprc_ctx_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return ms.value
 
     # device buffers (bench "value" leg: inputs resident in HBM)
     def malloc(self, nbytes):

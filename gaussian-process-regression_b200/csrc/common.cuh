@@ -72,6 +72,7 @@ struct gprc_ctx {
   };
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t marks[8] = {nullptr};
   long* d_info = nullptr;     // device scratch for LAPACK-style info
   double* d_scalars = nullptr;  // device scratch for small reductions (64 doubles)
   double* h_scalars = nullptr;  // pinned mirror

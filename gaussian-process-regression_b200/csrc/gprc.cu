@@ -239,6 +239,8 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
     cudaEventDestroy(p.b);
   }
   for (auto e : c->event_pool) cudaEventDestroy(e);
+  for (auto e : c->marks)
+    if (e) cudaEventDestroy(e);
   cudaFree(c->d_info);
   cudaFree(c->d_scalars);
   cudaFreeHost(c->h_scalars);
@@ -290,6 +292,23 @@ extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
   if (ms)
     for (int i = 0; i < GPRC_T_COUNT; ++i) ms[i] = c->timers[i];
   if (launches) *launches = c->launches;
+  return 0;
+}
+
+extern "C" int gprc_ctx_mark(gprc_ctx* c, int slot) {
+  GPRC_ARG(c != nullptr && slot >= 0 && slot < 8);
+  DeviceGuard g(c->device);
+  if (!c->marks[slot]) GPRC_CUDA(cudaEventCreate(&c->marks[slot]));
+  GPRC_CUDA(cudaEventRecord(c->marks[slot], c->stream));
+  return 0;
+}
+extern "C" int gprc_ctx_elapsed_ms(gprc_ctx* c, int a, int b, double* ms) {
+  GPRC_ARG(c != nullptr && ms != nullptr && a >= 0 && a < 8 && b >= 0 && b < 8 && c->marks[a] && c->marks[b]);
+  DeviceGuard g(c->device);
+  GPRC_CUDA(cudaEventSynchronize(c->marks[b]));
+  float f = 0.f;
+  GPRC_CUDA(cudaEventElapsedTime(&f, c->marks[a], c->marks[b]));
+  *ms = f;
   return 0;
 }
 

@@ -86,6 +86,9 @@ int gprc_ctx_set_option(gprc_ctx* ctx, int option, int value);
 int gprc_ctx_sync(gprc_ctx* ctx);
 void gprc_ctx_reset_timers(gprc_ctx* ctx);
 int gprc_ctx_get_timers(gprc_ctx* ctx, double* ms /* GPRC_T_COUNT */, long* kernel_launches);
+/* user event pair on the library's stream: device-side timing of an arbitrary region (bench.py) */
+int gprc_ctx_mark(gprc_ctx* ctx, int slot /* 0..7 */);
+int gprc_ctx_elapsed_ms(gprc_ctx* ctx, int slot_start, int slot_stop, double* ms);
 const char* gprc_last_error(void);
 int gprc_version(void);
 
