@@ -67,6 +67,9 @@ struct CovParams {
   const double* weights;   // nullable: pmean[tile_i][j] = sum_{i in tile} k(i, j) * weights[i]   (unscaled k)
   double* pmean;
   long ldpm;
+  // the same two fusions along the other axis (K_star^T builds: rows are test points, columns training points)
+  const double* colscale;    // nullable: stored value is colscale[j] * k
+  const double* colweights;  // nullable: pmean[tile_j][i] = sum_{j in tile} k(i, j) * colweights[j]
 };
 
 constexpr int CT = 64;    // covariance tile
@@ -77,7 +80,9 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const long ti = blockIdx.x, tj = blockIdx.y;
   if (p.lower_only && tj > ti) return;
-  __shared__ double As[CDCH][CT + 1], Bs[CDCH][CT + 1];
+  __shared__ double sh[2 * CDCH * (CT + 1)];  // one array: the row-sum reduction below reuses all of it
+  double (*As)[CT + 1] = reinterpret_cast<double (*)[CT + 1]>(sh);
+  double (*Bs)[CT + 1] = reinterpret_cast<double (*)[CT + 1]>(sh + CDCH * (CT + 1));
   const long i0 = ti * CT, j0 = tj * CT;
   double acc[4][4];
 #pragma unroll
@@ -126,6 +131,7 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
   }
 
   double msum[4] = {0.0, 0.0, 0.0, 0.0};  // per column b: sum over this thread's rows of k * weight
+  double rsum[4] = {0.0, 0.0, 0.0, 0.0};  // per row a: sum over this thread's columns of k * colweight
 #pragma unroll
   for (int qb = 0; qb < 4; ++qb) {
     const long gj = j0 + ty * 4 + qb;
@@ -137,7 +143,9 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
         v = (FAMILY == FAM_DIST) ? kfun_dist(p.k, acc[qa][qb]) : (FAMILY == FAM_DOT) ? kfun_dot(p.k, acc[qa][qb]) : p.k.c;
         if (p.symmetric && gi == gj) v += p.diag_add;
         if (p.weights) msum[qb] = fma(v, p.weights[gi], msum[qb]);
+        if (p.colweights) rsum[qa] = fma(v, p.colweights[gj], rsum[qa]);
         if (p.rowscale) v *= p.rowscale[gi];
+        if (p.colscale) v *= p.colscale[gj];
       } else {
         v = (p.pad_identity && gi == gj) ? 1.0 : 0.0;
       }
@@ -154,6 +162,20 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
       s += __shfl_xor_sync(0xffffffffu, s, 8);
       const long gj = j0 + ty * 4 + qb;
       if (tx == 0 && gj < p.cols_pad) p.pmean[ti * p.ldpm + gj] = s;
+    }
+  }
+  if (p.colweights) {
+    double* red = sh;  // 16 x 64 doubles <= 2 x 8 x 65
+    __syncthreads();
+#pragma unroll
+    for (int qa = 0; qa < 4; ++qa) red[ty * CT + tx + 16 * qa] = rsum[qa];
+    __syncthreads();
+    if (threadIdx.x < CT) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += red[q * CT + threadIdx.x];
+      const long gi = i0 + threadIdx.x;
+      if (gi < p.rows_pad) p.pmean[tj * p.ldpm + gi] = s;
     }
   }
 }

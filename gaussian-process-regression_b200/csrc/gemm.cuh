@@ -1,9 +1,10 @@
 // gemm.cuh -- the FP64 tensor-core (DMMA) GEMM core of libgprc and the tile policies built on it.
 //
-// One CTA (256 threads, 8 warps as 2 x 4) owns one 128 x 128 output tile; each warp owns 64 x 32 of it as
-// 8 x 4 m8n8k4 accumulator fragments (128 registers).  Operand k-slices (BK = 16) are staged in a 4-deep ring of
-// shared-memory buffers filled by the TMA engine with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) that complete
-// on per-stage mbarriers; rows are padded by 4 doubles so that every fragment load (LDS.64) is bank-conflict free.
+// One CTA (8 DMMA warps as 2 x 4, plus one producer warp) owns one 128 x 128 output tile; each DMMA warp owns 64 x 32
+// of it as 8 x 4 m8n8k4 accumulator fragments (128 registers).  Operand k-slices (BK = 16) are staged in a 4-deep ring
+// of shared-memory buffers that the producer warp fills through the TMA engine with 1-D bulk copies (cp.async.bulk ->
+// SASS UBLKCP) completing on per-stage "full" mbarriers; the DMMA warps hand a stage back through an "empty" mbarrier.
+// Rows are padded by 4 doubles so that every fragment load (LDS.64) is bank-conflict free.
 // FP64 DMMA runs at 64 FMA/clk/SM, i.e. one DMMA.8x8x4 per 16 clk per SM sub-partition, so the kernel is bound by
 // the tensor pipe: per k-slice a warp issues 12 LDS.64 for 32 DMMAs (19 % of the shared-memory bandwidth).
 //
@@ -19,14 +20,16 @@
 
 namespace gprc {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int GEMM_CONSUMERS = 256;                  // 8 DMMA warps
+constexpr int GEMM_THREADS = GEMM_CONSUMERS + 32;    // + 1 producer warp that only drives the TMA engine
 constexpr int LDA_S = BM + 4;     // MN-major tile [BK][LDA_S]: (lane%4)*132 mod 16 = {0,4,8,12} -> conflict free
 constexpr int LDB_MN_S = BN + 4;  // MN-major B tile [BK][LDB_MN_S]
 constexpr int LDB_K_S = BK + 4;   // K-major B tile [BN][LDB_K_S]: (lane/4)*20 mod 16 = {0,4,8,12} per half warp
 constexpr int A_STAGE_DOUBLES = BK * LDA_S;
 constexpr int B_STAGE_DOUBLES = (BN * LDB_K_S > BK * LDB_MN_S) ? BN * LDB_K_S : BK * LDB_MN_S;
 constexpr int STAGE_DOUBLES = A_STAGE_DOUBLES + B_STAGE_DOUBLES;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 64;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8 + 128;
 
 struct TileWork {
   const double* A;  // element (m, k) at A[m + k * lda], m in [0, 128)
@@ -42,7 +45,7 @@ struct WarpCoord {
   int lane, warp_m, warp_n;
   __device__ __forceinline__ WarpCoord() {
     lane = threadIdx.x & 31;
-    int w = threadIdx.x >> 5;
+    int w = (threadIdx.x >> 5) & 7;
     warp_m = w & 1;
     warp_n = w >> 1;
   }
@@ -51,33 +54,28 @@ struct WarpCoord {
   __device__ __forceinline__ int col(int nb, int r) const { return warp_n * 32 + nb * 8 + 2 * (lane & 3) + r; }
 };
 
+// barrier among the 8 consumer warps only (the producer warp has left the kernel by then)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// One k-slice, issued by ONE elected lane of the producer warp: announce the bytes (the barrier's single arrival),
+// then one bulk copy per contiguous run (1 KB runs for MN-major tiles, 128 B runs for the K-major B tile).
 template <bool B_KMAJOR>
-__device__ __forceinline__ void issue_stage(const TileWork& w, int k0, double* stage, uint32_t bar) {
-  const int tid = threadIdx.x;
-  uint32_t bytes = 0;
-  const void* src = nullptr;
-  uint32_t dst = 0;
-  if (tid < BK) {
-    src = w.A + (long)(k0 + tid) * w.lda;
-    dst = smem_u32(stage + tid * LDA_S);
-    bytes = BM * 8;
-  } else if (!B_KMAJOR) {
-    if (tid >= 32 && tid < 32 + BK) {
-      int r = tid - 32;
-      src = w.B + (long)(k0 + r) * w.ldb;
-      dst = smem_u32(stage + A_STAGE_DOUBLES + r * LDB_MN_S);
-      bytes = BN * 8;
-    }
+__device__ __forceinline__ void produce_stage(const TileWork& w, int k0, double* stage, uint32_t bar) {
+  constexpr uint32_t kBytes = (BM * BK + BN * BK) * 8;
+  mbar_arrive_expect_tx(bar, kBytes);
+  const uint32_t sa = smem_u32(stage), sb = smem_u32(stage + A_STAGE_DOUBLES);
+  const double* ap = w.A + (long)k0 * w.lda;
+#pragma unroll 4
+  for (int r = 0; r < BK; ++r) bulk_g2s(sa + r * (LDA_S * 8), ap + (long)r * w.lda, BM * 8, bar);
+  if (!B_KMAJOR) {
+    const double* bp = w.B + (long)k0 * w.ldb;
+#pragma unroll 4
+    for (int r = 0; r < BK; ++r) bulk_g2s(sb + r * (LDB_MN_S * 8), bp + (long)r * w.ldb, BN * 8, bar);
   } else {
-    if (tid >= 128) {
-      int r = tid - 128;
-      src = w.B + (long)r * w.ldb + k0;
-      dst = smem_u32(stage + A_STAGE_DOUBLES + r * LDB_K_S);
-      bytes = BK * 8;
-    }
+    const double* bp = w.B + k0;
+#pragma unroll 8
+    for (int r = 0; r < BN; ++r) bulk_g2s(sb + r * (LDB_K_S * 8), bp + (long)r * w.ldb, BK * 8, bar);
   }
-  mbar_arrive_expect_tx(bar, bytes);
-  if (bytes) bulk_g2s(dst, src, bytes, bar);
 }
 
 template <bool B_KMAJOR>
@@ -107,49 +105,55 @@ __device__ __forceinline__ void compute_stage(const double* __restrict__ stage, 
   }
 }
 
-// acc += A(128 x K) * B(K x 128) over k in [k_begin, k_end)
-template <bool B_KMAJOR>
-__device__ __forceinline__ void gemm_mainloop(const TileWork& w, Acc& acc, double* smem, uint64_t* bars) {
-  const WarpCoord wc;
-  const int KT = (w.k_end - w.k_begin) / BK;
-  if (KT <= 0) return;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(bars + s), GEMM_THREADS);
-    mbar_fence_init();
-  }
-  __syncthreads();
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s)
-    if (s < KT) issue_stage<B_KMAJOR>(w, w.k_begin + s * BK, smem + s * STAGE_DOUBLES, smem_u32(bars + s));
-  for (int kt = 0; kt < KT; ++kt) {
-    const int s = kt % STAGES;
-    mbar_wait(smem_u32(bars + s), (kt / STAGES) & 1);
-    __syncthreads();  // every warp has finished reading the stage that is refilled below (consumed at kt - 1)
-    const int kn = kt + STAGES - 1;
-    if (kn < KT) {
-      const int sn = kn % STAGES;
-      issue_stage<B_KMAJOR>(w, w.k_begin + kn * BK, smem + sn * STAGE_DOUBLES, smem_u32(bars + sn));
-    }
-    compute_stage<B_KMAJOR>(smem + s * STAGE_DOUBLES, wc, acc);
-  }
-}
-
+// Warp-specialised mainloop.  full[s]: TMA bytes landed (1 arrival + tx count); empty[s]: all 8 consumer warps have
+// finished reading stage s.  No block-wide barrier inside the loop: the DMMA warps drift freely, so one warp's wait is
+// covered by the other warp of its SM sub-partition.
 template <class Policy>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const Policy p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_DOUBLES * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + STAGES;
   TileWork w;
   typename Policy::Tile t;
   if (!p.setup(w, t)) return;  // depends on blockIdx only: uniform for the CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KT = (w.k_end - w.k_begin) / BK;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), GEMM_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == GEMM_CONSUMERS / 32) {
+    // ===== producer warp =====
+    if (lane == 0) {
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        if (kt >= STAGES) mbar_wait(smem_u32(empty + s), ((kt / STAGES) - 1) & 1);
+        produce_stage<Policy::B_KMAJOR>(w, w.k_begin + kt * BK, smem + s * STAGE_DOUBLES, smem_u32(full + s));
+      }
+    }
+    return;
+  }
+  // ===== consumer warps =====
   Acc acc;
 #pragma unroll
   for (int mb = 0; mb < 8; ++mb)
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
   p.prefetch(t);
-  gemm_mainloop<Policy::B_KMAJOR>(w, acc, smem, bars);
+  const WarpCoord wc;
+  for (int kt = 0; kt < KT; ++kt) {
+    const int s = kt % STAGES;
+    mbar_wait(smem_u32(full + s), (kt / STAGES) & 1);
+    compute_stage<Policy::B_KMAJOR>(smem + s * STAGE_DOUBLES, wc, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(empty + s));
+  }
   p.epilogue(t, acc, smem);
 }
 
@@ -198,7 +202,7 @@ struct SyrkPolicy {
     // pull the C tile (128 columns x 8 lines of 128 B) into L2 while the mainloop runs: 4 lines per thread
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      int line = threadIdx.x + q * GEMM_THREADS;
+      int line = threadIdx.x + q * GEMM_CONSUMERS;
       prefetch_l2(t.C + (long)(line >> 3) * ld + (line & 7) * 16);
     }
   }
@@ -345,18 +349,19 @@ struct Trtri2Policy {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Predictive variance:  V = W * Ks  (W = L^-1 lower triangular n x n, Ks n x mc col-major), never stored: the
-// epilogue reduces the squares of each tile column and writes partial[ti][column]  (R/GPRclass.R:162-164:
-// v <- solve(L, K_star); colSums(v * v)).  Tiles are issued heaviest first (largest row tile = longest k range)
-// in groups of GROUP row tiles so that one wave of CTAs shares both W row panels and Ks column panels in L2.
+// Predictive variance:  V = W * Ks  (W = L^-1 lower triangular n x n; Ks given TRANSPOSED, KsT mc x n with the test
+// point contiguous, so that both operands stream in 1 KB runs), never stored: the epilogue reduces the squares of each
+// tile column and writes partial[ti][column]  (R/GPRclass.R:162-164: v <- solve(L, K_star); colSums(v * v)).
+// Tiles are issued heaviest first (largest row tile = longest k range) in groups of GROUP row tiles so that one wave
+// of CTAs shares both W row panels and Ks column panels in L2.
 // If VoutT != nullptr the tile of V is stored as well, transposed (full predictive covariance, R/GPRclass.R:167).
 // ---------------------------------------------------------------------------------------------------------------
 struct TrmmNormPolicy {
-  static constexpr bool B_KMAJOR = true;
+  static constexpr bool B_KMAJOR = false;
   static constexpr int GROUP = 8;
   const double* W;
   long ldw;
-  const double* Ks;
+  const double* KsT;  // element (k, t) at KsT[t + k * ldk]
   long ldk;
   double* partial;  // [nt][ldp]
   long ldp;
@@ -379,7 +384,7 @@ struct TrmmNormPolicy {
     t.tc = tc;
     w.A = W + (long)t.ti * NB;
     w.lda = ldw;
-    w.B = Ks + (long)tc * NB * ldk;
+    w.B = KsT + (long)tc * NB;
     w.ldb = ldk;
     w.k_begin = 0;
     w.k_end = (t.ti + 1) * NB;
@@ -398,7 +403,7 @@ struct TrmmNormPolicy {
           *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
       }
     }
-    __syncthreads();  // all stages consumed; shared memory is reused for the cross-warp reduction
+    consumer_sync();  // every consumer warp is past its last stage: shared memory is reused for the reduction
     double* red = smem;  // [2][128]
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb)
@@ -412,7 +417,7 @@ struct TrmmNormPolicy {
         s += __shfl_xor_sync(0xffffffffu, s, 16);
         if ((wc.lane >> 2) == 0) red[wc.warp_m * 128 + wc.col(nb, r)] = s;
       }
-    __syncthreads();
+    consumer_sync();
     if (threadIdx.x < 128)
       partial[(long)t.ti * ldp + (long)t.tc * NB + threadIdx.x] = red[threadIdx.x] + red[128 + threadIdx.x];
   }

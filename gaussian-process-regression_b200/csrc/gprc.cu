@@ -131,6 +131,24 @@ __global__ void __launch_bounds__(256) gemv_t_rect_kernel(const double* __restri
   if (lane == 0) y[col] = s;
 }
 
+// dst[t + k * ldt] = (k < n && t < m) ? src[k + t * lds] * (scale ? scale[k] : 1) : 0  over k < n_pad, t < m_pad
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const double* __restrict__ src, long lds, long n, long m,
+                                                            double* __restrict__ dst, long ldt, long n_pad, long m_pad,
+                                                            const double* __restrict__ scale) {
+  __shared__ double tile[32][33];
+  const long k0 = blockIdx.x * 32L, t0 = blockIdx.y * 32L;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int q = ty; q < 32; q += 8) {
+    const long k = k0 + tx, t = t0 + q;
+    tile[q][tx] = (k < n && t < m) ? src[k + t * lds] * (scale ? scale[k] : 1.0) : 0.0;
+  }
+  __syncthreads();
+  for (int q = ty; q < 32; q += 8) {
+    const long t = t0 + tx, k = k0 + q;
+    if (t < m_pad && k < n_pad) dst[t + k * ldt] = tile[tx][q];
+  }
+}
+
 static inline dim3 grid2(long rows, long cols) { return dim3((unsigned)((rows + 255) / 256), (unsigned)cols); }
 
 }  // namespace gprc
@@ -142,7 +160,7 @@ using namespace gprc;
 // =================================================================================================================
 struct PredictWorkspace {
   long mc = 0;          // chunk capacity (multiple of 128)
-  double* Ks = nullptr;     // n_pad x mc
+  double* Ks = nullptr;     // K_star^T: mc x n_pad (test point contiguous, leading dimension mc)
   double* pmean = nullptr;  // (n_pad / 64) x mc
   double* pvar = nullptr;   // (n_pad / 128) x mc
   double* kss = nullptr;    // mc
@@ -355,7 +373,8 @@ extern "C" int gprc_host_unregister(void* host) {
 static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d, long nA, const double* dB, long nB,
                          double* out, long ldo, long rows_pad, long cols_pad, bool lower_only, bool symmetric,
                          double diag_add, bool pad_identity, const double* rowscale, const double* weights,
-                         double* pmean, long ldpm) {
+                         double* pmean, long ldpm, const double* colscale = nullptr,
+                         const double* colweights = nullptr) {
   CovParams p;
   p.k = k;
   p.A = dA;
@@ -375,6 +394,8 @@ static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d
   p.weights = weights;
   p.pmean = pmean;
   p.ldpm = ldpm;
+  p.colscale = colscale;
+  p.colweights = colweights;
   return launch_cov(c, p);
 }
 
@@ -509,8 +530,8 @@ static int variance_pass(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long
   TrmmNormPolicy p;
   p.W = F.W;
   p.ldw = F.n_pad;
-  p.Ks = ws.Ks;
-  p.ldk = F.n_pad;
+  p.KsT = ws.Ks;
+  p.ldk = ws.mc;
   p.partial = ws.pvar;
   p.ldp = ws.mc;
   p.VoutT = VoutT;
@@ -533,8 +554,10 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     const long mpad = round_up(mcur, NB);
     {
       PhaseTimer t(c, GPRC_T_BUILD_KS);
-      GPRC_CHECK(cov_build_dev(c, k, dX, d, F.n, dXs + c0 * d, mcur, ws.Ks, F.n_pad, F.n_pad, mpad, false, false, 0.0,
-                               false, rowscale, weights, ws.pmean, ws.mc));
+      // K_star^T tile by tile: rows = test points, columns = training points; sqrt(W) scaling and the mean's
+      // weighted sums run along the training axis
+      GPRC_CHECK(cov_build_dev(c, k, dXs + c0 * d, d, mcur, dX, F.n, ws.Ks, ws.mc, mpad, F.n_pad, false, false, 0.0,
+                               false, nullptr, nullptr, ws.pmean, ws.mc, rowscale, weights));
       cov_pointwise_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(k, dXs + c0 * d, dXs + c0 * d, d,
                                                                                  mcur, ws.kss);
       c->launches++;
@@ -555,23 +578,20 @@ static int predict_precomputed(gprc_ctx* c, FactorState& F, PredictWorkspace& ws
                                double* var) {
   GPRC_CHECK(ensure_inverse(c, F));
   GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
-  double *dmean = nullptr, *dvar = nullptr;
+  double *dmean = nullptr, *dvar = nullptr, *stage = nullptr;
   GPRC_CHECK(dmalloc(&dmean, (size_t)ws.mc));
   GPRC_CHECK(dmalloc(&dvar, (size_t)ws.mc));
+  GPRC_CHECK(dmalloc(&stage, (size_t)F.n * std::min<long>(ws.mc, m)));
   int rc = 0;
   for (long c0 = 0; c0 < m && rc == 0; c0 += ws.mc) {
     const long mcur = std::min(ws.mc, m - c0);
     const long mpad = round_up(mcur, NB);
-    cudaMemsetAsync(ws.Ks, 0, sizeof(double) * F.n_pad * mpad, c->stream);
-    cudaMemcpy2DAsync(ws.Ks, F.n_pad * sizeof(double), Ks + c0 * F.n, F.n * sizeof(double), F.n * sizeof(double), mcur,
-                      cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(stage, Ks + c0 * F.n, sizeof(double) * F.n * mcur, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(ws.kss, kss + c0, sizeof(double) * mcur, cudaMemcpyHostToDevice, c->stream);
-    gemv_t_rect_kernel<<<(unsigned)((mcur + 7) / 8), 256, 0, c->stream>>>(ws.Ks, F.n_pad, F.n, mcur, weights, dmean);
-    c->launches++;
-    if (rowscale) {
-      scale_rows_kernel<<<grid2(F.n, mcur), 256, 0, c->stream>>>(ws.Ks, F.n_pad, F.n, mcur, rowscale);
-      c->launches++;
-    }
+    gemv_t_rect_kernel<<<(unsigned)((mcur + 7) / 8), 256, 0, c->stream>>>(stage, F.n, F.n, mcur, weights, dmean);
+    transpose_pad_kernel<<<dim3((unsigned)(F.n_pad / 32), (unsigned)(mpad / 32)), 256, 0, c->stream>>>(
+        stage, F.n, F.n, mcur, ws.Ks, ws.mc, F.n_pad, mpad, rowscale);
+    c->launches += 2;
     if ((rc = variance_pass(c, F, ws, mpad, nullptr, 0))) break;
     finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
         nullptr, 0, 0, ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, nullptr, dvar);
@@ -583,6 +603,7 @@ static int predict_precomputed(gprc_ctx* c, FactorState& F, PredictWorkspace& ws
   }
   dfree(dmean);
   dfree(dvar);
+  dfree(stage);
   return rc;
 }
 
@@ -793,7 +814,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
   double *dXs = nullptr, *dmean = nullptr, *dVt = nullptr, *dS = nullptr;
   int rc = 0;
   do {
-    if ((rc = dmalloc(&ws.Ks, (size_t)F.n_pad * mp))) break;
+    if ((rc = dmalloc(&ws.Ks, (size_t)F.n_pad * mp))) break;  // K_star^T, mp x n_pad
     if ((rc = dmalloc(&ws.pmean, (size_t)(F.n_pad / CT) * mp))) break;
     if ((rc = dmalloc(&ws.pvar, (size_t)(F.n_pad / NB) * mp))) break;
     if ((rc = dmalloc(&ws.kss, (size_t)mp))) break;
@@ -805,8 +826,8 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
     cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
     {
       PhaseTimer t(c, GPRC_T_BUILD_KS);
-      if ((rc = cov_build_dev(c, g->spec.dev, g->X, g->d, F.n, dXs, m, ws.Ks, F.n_pad, F.n_pad, mp, false, false, 0.0,
-                              false, nullptr, g->alpha, ws.pmean, ws.mc)))
+      if ((rc = cov_build_dev(c, g->spec.dev, dXs, g->d, m, g->X, F.n, ws.Ks, mp, mp, F.n_pad, false, false, 0.0,
+                              false, nullptr, nullptr, ws.pmean, ws.mc, nullptr, g->alpha)))
         break;
       // Sigma starts as covariance_matrix(X_star, X_star, k); zero padding
       if ((rc = cov_build_dev(c, g->spec.dev, dXs, g->d, m, dXs, m, dS, mp, mp, mp, false, false, 0.0, false, nullptr,
