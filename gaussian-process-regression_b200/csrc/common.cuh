@@ -61,6 +61,8 @@ struct DevBuf {
 struct gprc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_hi = nullptr;  // high priority: the latency-bound panel factorisation (Cholesky lookahead)
+  cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr;
   int sm_count = 148;
   int opt_gram_dmma = 1;
   long launches = 0;

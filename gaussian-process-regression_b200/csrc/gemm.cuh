@@ -270,12 +270,16 @@ struct TrsmPolicy {
 // [2 s g, 2 s g + s) (left, W11 known) and [2 s g + s, min(2 s g + 2 s, nt)) (right, W22 known):
 //   phase 1:  T   = L21 * W11      (k >= column tile: W11 is lower triangular)   stored TRANSPOSED in S
 //   phase 2:  W21 = - W22 * T      (k <= row tile: W22 is lower triangular)
+// W11 enters phase 1 as the "B" operand, element (k, c) = W11[k, c]; read from W itself that is a K-major operand
+// (128-byte runs, which the TMA engine serves at only ~1 request / 54 clk).  So the inversion also maintains
+// Wt = W^T (upper triangular): W11[k, c] = Wt[c + k ld] is MN-major and streams in 1 KB runs; phase 2 writes every
+// new tile to both W and Wt.
 // grid = (s, s, groups): blockIdx.x = column tile tj, blockIdx.y = row tile ti (within the right part)
 // ---------------------------------------------------------------------------------------------------------------
 struct Trtri1Policy {
-  static constexpr bool B_KMAJOR = true;
+  static constexpr bool B_KMAJOR = false;
   const double* L;
-  const double* W;
+  const double* Wt;
   double* S;
   long ld;
   int s, nt;
@@ -289,7 +293,7 @@ struct Trtri1Policy {
     if (ti >= r) return false;
     w.A = L + (long)(gr + ti) * NB + (long)gl * NB * ld;
     w.lda = ld;
-    w.B = W + (long)gl * NB + (long)(gl + tj) * NB * ld;
+    w.B = Wt + (long)(gl + tj) * NB + (long)gl * NB * ld;  // element (k, n) = W11[k, n] = Wt[n + k ld]
     w.ldb = ld;
     w.k_begin = tj * NB;
     w.k_end = s * NB;
@@ -303,10 +307,8 @@ struct Trtri1Policy {
     for (int mb = 0; mb < 8; ++mb) {
       double* cp = t.C + (long)wc.row(mb) * ld;  // row of T -> column of S
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        double2 v = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = v;
-      }
+      for (int nb = 0; nb < 4; ++nb)
+        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
     }
   }
 };
@@ -314,11 +316,13 @@ struct Trtri1Policy {
 struct Trtri2Policy {
   static constexpr bool B_KMAJOR = false;
   double* W;
+  double* Wt;
   const double* S;
   long ld;
   int s, nt;
   struct Tile {
     double* C;
+    double* Ct;
   };
   __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
     const int g = blockIdx.z, tj = blockIdx.x, ti = blockIdx.y;
@@ -332,6 +336,7 @@ struct Trtri2Policy {
     w.k_begin = 0;
     w.k_end = (ti + 1) * NB;
     t.C = W + (long)(gr + ti) * NB + (long)(gl + tj) * NB * ld;
+    t.Ct = Wt + (long)(gl + tj) * NB + (long)(gr + ti) * NB * ld;
     return true;
   }
   __device__ __forceinline__ void prefetch(const Tile&) const {}
@@ -345,6 +350,13 @@ struct Trtri2Policy {
 #pragma unroll
         for (int mb = 0; mb < 8; ++mb) cp[wc.row(mb)] = -acc[mb][nb][r];
       }
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+      double* cp = t.Ct + (long)wc.row(mb) * ld;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = make_double2(-acc[mb][nb][0], -acc[mb][nb][1]);
+    }
   }
 };
 
@@ -471,14 +483,15 @@ struct DgemmPolicy {
 };
 
 template <class Policy>
-inline int launch_gemm(gprc_ctx* ctx, const Policy& p, dim3 grid) {
+inline int launch_gemm(gprc_ctx* ctx, const Policy& p, dim3 grid, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ctx->stream;
   static bool configured[64] = {false};
   if (!configured[ctx->device & 63]) {
     GPRC_CUDA(cudaFuncSetAttribute(gemm_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     configured[ctx->device & 63] = true;
   }
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
-  gemm_kernel<Policy><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(p);
+  gemm_kernel<Policy><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
   ctx->launches++;
   GPRC_CUDA(cudaGetLastError());
   return 0;

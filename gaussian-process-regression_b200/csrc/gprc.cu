@@ -239,7 +239,13 @@ extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
   gprc_ctx* c = new gprc_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  GPRC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  GPRC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GPRC_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+  GPRC_CUDA(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, prio_hi));
+  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
   GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
@@ -263,6 +269,11 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
   cudaFree(c->d_scalars);
   cudaFreeHost(c->h_scalars);
   cudaFreeHost(c->h_info);
+  cudaStreamSynchronize(c->stream_hi);
+  cudaEventDestroy(c->ev_start);
+  cudaEventDestroy(c->ev_panel);
+  cudaEventDestroy(c->ev_rest);
+  cudaStreamDestroy(c->stream_hi);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -498,9 +509,14 @@ static int ensure_inverse(gprc_ctx* c, FactorState& F) {
   GPRC_CHECK(dmalloc(&F.W, (size_t)F.n_pad * F.n_pad));
   PhaseTimer t(c, GPRC_T_TRTRI);
   GPRC_CUDA(cudaMemsetAsync(F.W, 0, sizeof(double) * F.n_pad * F.n_pad, c->stream));  // zeros above the diagonal
-  // scratch for the level products aliases the (unused) strictly upper block triangle of the L buffer
-  GPRC_CHECK(trtri_levels(c, F.L, F.n_pad, F.n_pad, F.dinv, F.W, F.L));
-  return 0;
+  // scratch for the level products aliases the (unused) strictly upper block triangle of the L buffer;
+  // W^T is only needed while inverting
+  double* Wt = nullptr;
+  GPRC_CHECK(dmalloc(&Wt, (size_t)F.n_pad * F.n_pad));
+  int rc = trtri_levels(c, F.L, F.n_pad, F.n_pad, F.dinv, F.W, Wt, F.L);
+  cudaStreamSynchronize(c->stream);
+  dfree(Wt);
+  return rc;
 }
 
 static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m) {
@@ -1367,6 +1383,14 @@ extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, co
                               double* dscratch) {
   GPRC_ARG(c && dL && dinv && dW && dscratch && n > 0 && n % NB == 0 && ld % NB == 0 && ld >= n);
   DeviceGuard guard(c->device);
-  PhaseTimer t(c, GPRC_T_TRTRI);
-  return trtri_levels(c, dL, n, ld, dinv, dW, dscratch);
+  double* Wt = nullptr;
+  GPRC_CHECK(dmalloc(&Wt, (size_t)n * ld));
+  int rc;
+  {
+    PhaseTimer t(c, GPRC_T_TRTRI);
+    rc = trtri_levels(c, dL, n, ld, dinv, dW, Wt, dscratch);
+  }
+  cudaStreamSynchronize(c->stream);
+  dfree(Wt);
+  return rc;
 }

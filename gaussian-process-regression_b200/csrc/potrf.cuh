@@ -2,12 +2,13 @@
 // inversion of its factor.  Replaces t(chol(K + new_noise * diag(n))) of R/GPRclass.R:142, R/fit.R:121 and
 // R/GPCclass.R:80,102.
 //
-// Structure (nb = 128, outer panel = 4 blocks = 512 columns):
+// Structure (nb = 128, outer panel = 4 blocks = 512 columns; see potrf_blocked for the two-stream lookahead):
 //   for each outer panel J:
 //     for each block column j in J:
 //        left update   A[j:, j] -= A[j:, J0:j] A[j, J0:j]^T        DMMA GEMM, K <= 384           (SyrkPolicy mode 0)
-//        potrf_diag    factor the 128 x 128 diagonal block in shared memory, invert it in place
-//                      (warp-shuffle-free column sweep; reports the first non-positive pivot in `info`)
+//        potrf_diag    factor the 128 x 128 diagonal block in shared memory and invert it in place (8-column inner
+//                      blocks: DMMA updates from shared memory, warp-shuffle 8 x 8 pivot blocks); reports the first
+//                      non-positive pivot in `info`
 //        panel solve   A[j+1:, j] = A[j+1:, j] Linv_j^T              DMMA GEMM, K = 128            (TrsmPolicy)
 //     trailing update  A[Jend:, Jend:] -= A[Jend:, J] A[Jend:, J]^T  DMMA SYRK on lower tiles, K = 512 (mode 1)
 // Every trailing element is read and written once per 512 columns (64 flop/byte), so the factorisation is bound by
@@ -17,77 +18,180 @@
 
 namespace gprc {
 
-constexpr int PD_LDS = NB + 1;
-constexpr int PD_SMEM_BYTES = NB * PD_LDS * 8;
+constexpr int PD_LDS = NB + 4;  // 132: DMMA fragment reads are bank-conflict free along rows and along columns
+constexpr int PD_SMEM_BYTES = (NB * PD_LDS + NB) * 8;
 constexpr int OUTER_BLOCKS = 4;
+constexpr int PB = 8;            // inner block of the diagonal-block factorisation = one DMMA tile
+constexpr int PNB = NB / PB;     // 16
 
 // Factor the diagonal block j of A (lower, in place; zeros written above the diagonal of the block) and write
 // the inverse of the factor to linv (128 x 128 col-major, zeros above the diagonal).
 // info: atomicMin of the 1-based global index of the first pivot that is not > 0 (LAPACK dpotrf convention).
+//
+// The block lives in shared memory (S[c * 132 + r]).  Factorisation is left-looking over 16 inner blocks of 8 columns:
+//   (a) the 8-column panel is updated with everything to its left by m8n8k4 DMMAs straight from shared memory,
+//   (b) warp 0 factors the 8 x 8 pivot block in registers, exchanging pivots and multipliers with warp shuffles,
+//   (c) one thread per row solves its 8 entries of the panel against the pivot block.
+// The inverse is then formed in place: 8 x 8 diagonal blocks by substitution, and W21 = -W22 (L21 W11) level by level
+// (block sizes 8, 16, 32, 64) again with DMMAs; the product T = L21 W11 is parked in the mirrored upper block.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int j, double* linv, long* info,
                                                          double* diag_out /* nullable: L_ii for this block */) {
   extern __shared__ __align__(16) unsigned char pd_raw[];
   double* S = reinterpret_cast<double*>(pd_raw);  // S[c * PD_LDS + r]
+  double* rdiag = S + NB * PD_LDS;                // 1 / L_ii
   double* Ajj = A + (long)j * NB * (ld + 1);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lk = lane & 3, lr = lane >> 2;
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e & (NB - 1), c = e >> 7;
     S[c * PD_LDS + r] = (r >= c) ? Ajj[r + (long)c * ld] : 0.0;
   }
-  const int i = tid & (NB - 1), half = tid >> 7;
-  for (int c = 0; c < NB; ++c) {
-    __syncthreads();
-    const double d = S[c * PD_LDS + c];
-    if (!(d > 0.0)) {
-      if (tid == 0) atomicMin(reinterpret_cast<unsigned long long*>(info), (unsigned long long)((long)j * NB + c + 1));
+  __syncthreads();
+
+  for (int jb = 0; jb < PNB; ++jb) {
+    const int c0 = jb * PB;
+    if (jb > 0) {
+      // (a) S[rt*8.., c0..c0+8) -= L[rt*8.., 0:c0) L[c0..c0+8, 0:c0)^T  for the row tiles rt >= jb
+      for (int rt = jb + warp; rt < PNB; rt += 8) {
+        double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;  // two accumulator pairs: halves the dependent DMMA chain
+        const double* ap = S + lk * PD_LDS + rt * PB + lr;
+        const double* bp = S + lk * PD_LDS + c0 + lr;
+        for (int k0 = 0; k0 + 8 <= c0; k0 += 8) {
+          dmma884(e0, e1, ap[k0 * PD_LDS], bp[k0 * PD_LDS]);
+          dmma884(o0, o1, ap[(k0 + 4) * PD_LDS], bp[(k0 + 4) * PD_LDS]);
+        }
+        double* cp = S + (c0 + 2 * lk) * PD_LDS + rt * PB + lr;
+        cp[0] -= e0 + o0;
+        cp[PD_LDS] -= e1 + o1;
+      }
+      __syncthreads();
     }
-    const double r = sqrt(d);
-    const double rinv = 1.0 / r;
-    double li = 0.0;
-    if (i > c) {
-      li = S[c * PD_LDS + i] * rinv;
-      for (int cc = c + 1 + half; cc <= i; cc += 2) {
-        const double lc = S[c * PD_LDS + cc] * rinv;
-        S[cc * PD_LDS + i] = fma(-li, lc, S[cc * PD_LDS + i]);
+    if (warp == 0) {
+      // (b) 8 x 8 pivot block: lane (row = lane & 7) holds its row; lanes 8..31 mirror lanes 0..7
+      const int row = lane & 7;
+      double a[PB];
+#pragma unroll
+      for (int q = 0; q < PB; ++q) a[q] = S[(c0 + q) * PD_LDS + c0 + row];
+#pragma unroll
+      for (int kk = 0; kk < PB; ++kk) {
+        const double d = __shfl_sync(0xffffffffu, a[kk], kk);
+        if (!(d > 0.0) && lane == 0)
+          atomicMin(reinterpret_cast<unsigned long long*>(info), (unsigned long long)((long)j * NB + c0 + kk + 1));
+        const double r = sqrt(d);
+        const double rinv = 1.0 / r;
+        const double l = a[kk] * rinv;
+        if (row == kk) {
+          a[kk] = r;
+          if (lane < PB) rdiag[c0 + kk] = rinv;
+        } else if (row > kk) {
+          a[kk] = l;
+        }
+#pragma unroll
+        for (int cc = kk + 1; cc < PB; ++cc) {
+          const double lcc = __shfl_sync(0xffffffffu, l, cc);
+          if (row >= cc) a[cc] = fma(-l, lcc, a[cc]);
+        }
+      }
+      if (lane < PB) {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) S[(c0 + q) * PD_LDS + c0 + row] = (q <= row) ? a[q] : 0.0;
       }
     }
     __syncthreads();
-    if (half == 0) {
-      if (i > c) S[c * PD_LDS + i] = li;
-      if (i == c) S[c * PD_LDS + c] = r;
+    // (c) rows below the pivot block: x Ld^T = a  (forward substitution along the row's 8 entries)
+    if (tid < NB && tid >= c0 + PB) {
+      double x[PB];
+#pragma unroll
+      for (int q = 0; q < PB; ++q) {
+        double v = S[(c0 + q) * PD_LDS + tid];
+#pragma unroll
+        for (int pp = 0; pp < q; ++pp) v = fma(-x[pp], S[(c0 + pp) * PD_LDS + c0 + q], v);
+        x[q] = v * rdiag[c0 + q];
+      }
+#pragma unroll
+      for (int q = 0; q < PB; ++q) S[(c0 + q) * PD_LDS + tid] = x[q];
     }
+    __syncthreads();
   }
-  __syncthreads();
-  // write L back (explicit zeros above the diagonal of the block)
+  // write L back (explicit zeros above the diagonal: the strictly upper part was loaded as zero and never touched)
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e & (NB - 1), c = e >> 7;
     Ajj[r + (long)c * ld] = S[c * PD_LDS + r];
   }
   if (diag_out && tid < NB) diag_out[(long)j * NB + tid] = S[tid * PD_LDS + tid];
+
+  // ---- in-place inversion ----
+  // (d) 8 x 8 diagonal blocks: thread = (block b, column c) solves Ld w = e_c
+  double wcol[PB];
+  const int ib = tid >> 3, ic = tid & 7;
+  if (tid < NB) {
+    const double* Ld = S + (ib * PB) * PD_LDS + ib * PB;  // Ld[i][k] = Ld[k * PD_LDS + i]
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      double acc = (i == ic) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) acc = fma(-Ld[k * PD_LDS + i], wcol[k], acc);
+      wcol[i] = (i >= ic) ? acc * rdiag[ib * PB + i] : 0.0;
+    }
+  }
   __syncthreads();
-  // in-place inversion of the lower-triangular factor (LAPACK dtrti2, lower): columns from the last to the first;
-  //   W[c][c] = 1 / L[c][c];  W[c+1:, c] = -W[c][c] * (W[c+1:, c+1:] * L[c+1:, c])
-  for (int c = NB - 1; c >= 0; --c) {
-    double y = 0.0;
-    const double wcc = 1.0 / S[c * PD_LDS + c];
-    if (half == 0 && i > c) {
-      for (int k = c + 1; k <= i; ++k) y = fma(S[k * PD_LDS + i], S[c * PD_LDS + k], y);  // W[i][k] * L[k][c]
+  if (tid < NB) {
+#pragma unroll
+    for (int i = 0; i < PB; ++i) S[(ib * PB + ic) * PD_LDS + ib * PB + i] = wcol[i];
+  }
+  __syncthreads();
+  // (e) levels: left part [gl, gl + s), right part [gr, gr + s) in units of 8
+  for (int s = 1; s < PNB; s *= 2) {
+    const int tiles = (PNB / (2 * s)) * s * s;
+    // phase 1: T = L21 W11, stored at the mirrored (strictly upper) position S[(gr*8 + x) * LDS + gl*8 + y] = T[x][y]
+    for (int q = warp; q < tiles; q += 8) {
+      const int g = q / (s * s), rem = q - g * s * s, ti = rem / s, tj = rem - ti * s;
+      const int gl = 2 * s * g, gr = gl + s;
+      double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+      const double* ap = S + ((gl + tj) * PB + lk) * PD_LDS + (gr + ti) * PB + lr;   // L21[row][k], k from tile tj
+      const double* bp = S + ((gl + tj) * PB + lr) * PD_LDS + (gl + tj) * PB + lk;   // W11[k][col]
+      for (int kb = tj; kb < s; ++kb) {
+        const int ko = (kb - tj) * PB;
+        dmma884(e0, e1, ap[ko * PD_LDS], bp[ko]);
+        dmma884(o0, o1, ap[(ko + 4) * PD_LDS], bp[ko + 4]);
+      }
+      double* cp = S + ((gr + ti) * PB + lr) * PD_LDS + (gl + tj) * PB + 2 * lk;
+      cp[0] = e0 + o0;
+      cp[1] = e1 + o1;
     }
     __syncthreads();
-    if (half == 0) {
-      if (i > c) S[c * PD_LDS + i] = -wcc * y;
-      if (i == c) S[c * PD_LDS + c] = wcc;
+    // phase 2: W21 = -W22 T, overwriting L21
+    for (int q = warp; q < tiles; q += 8) {
+      const int g = q / (s * s), rem = q - g * s * s, ti = rem / s, tj = rem - ti * s;
+      const int gl = 2 * s * g, gr = gl + s;
+      double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+      const double* ap = S + (gr * PB + lk) * PD_LDS + (gr + ti) * PB + lr;   // W22[row][k]
+      const double* bp = S + (gr * PB + lk) * PD_LDS + (gl + tj) * PB + lr;   // T[k][col]
+      for (int kb = 0; kb <= ti; ++kb) {
+        const int ko = kb * PB;
+        dmma884(e0, e1, ap[ko * PD_LDS], bp[ko * PD_LDS]);
+        dmma884(o0, o1, ap[(ko + 4) * PD_LDS], bp[(ko + 4) * PD_LDS]);
+      }
+      double* cp = S + ((gl + tj) * PB + 2 * lk) * PD_LDS + (gr + ti) * PB + lr;
+      cp[0] = -(e0 + o0);
+      cp[PD_LDS] = -(e1 + o1);
     }
     __syncthreads();
   }
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e & (NB - 1), c = e >> 7;
-    linv[e] = S[c * PD_LDS + r];  // linv[r + c * 128]; strictly upper entries are still the zeros loaded above
+    linv[e] = (r >= c) ? S[c * PD_LDS + r] : 0.0;  // the upper part holds scratch of the level products
   }
 }
 
 // In-place Cholesky of the lower triangle of A (n, ld multiples of 128).  dinv receives the inverted diagonal blocks,
-// ddiag (nullable) the diagonal of L.  d_info must be initialised to LONG_MAX-like sentinel by the caller.
+// ddiag (nullable) the diagonal of L.  d_info must be initialised to a LONG_MAX sentinel by the caller.
+//
+// Lookahead over two streams: the latency-bound factorisation of outer panel P + 1 (left updates, potrf_diag, panel
+// solves) runs on a high-priority stream while the main stream applies outer panel P to everything right of panel
+// P + 1; the narrow update of panel P + 1's own columns ("LA") goes first on the high-priority stream.
+//   s1:  panel(0) | LA(0) panel(1) | LA(1) panel(2) | ...
+//   s0:           | rest(0)        | rest(1)        | ...        rest(P) waits panel(P); LA(P) waits rest(P - 1)
 inline int potrf_blocked(gprc_ctx* ctx, double* A, long n, long ld, double* dinv, long* d_info, double* ddiag) {
   static bool configured[64] = {false};
   if (!configured[ctx->device & 63]) {
@@ -95,50 +199,81 @@ inline int potrf_blocked(gprc_ctx* ctx, double* A, long n, long ld, double* dinv
     configured[ctx->device & 63] = true;
   }
   const int nt = (int)(n / NB);
-  for (int J0 = 0; J0 < nt; J0 += OUTER_BLOCKS) {
-    const int Jend = (J0 + OUTER_BLOCKS < nt) ? J0 + OUTER_BLOCKS : nt;
+  cudaStream_t s0 = ctx->stream, s1 = ctx->stream_hi;
+  GPRC_CUDA(cudaEventRecord(ctx->ev_start, s0));
+  GPRC_CUDA(cudaStreamWaitEvent(s1, ctx->ev_start, 0));
+
+  auto panel = [&](int J0, int Jend) -> int {
     for (int j = J0; j < Jend; ++j) {
       if (j > J0) {
         SyrkPolicy p{A, ld, 0, j, J0 * NB, j * NB};
-        GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - j)));
+        GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - j), s1));
       }
-      potrf_diag_kernel<<<1, 256, PD_SMEM_BYTES, ctx->stream>>>(A, ld, j, dinv + (long)j * NB * NB, d_info, ddiag);
+      potrf_diag_kernel<<<1, 256, PD_SMEM_BYTES, s1>>>(A, ld, j, dinv + (long)j * NB * NB, d_info, ddiag);
       ctx->launches++;
       GPRC_CUDA(cudaGetLastError());
       if (j + 1 < nt) {
         TrsmPolicy p{A, ld, dinv + (long)j * NB * NB, j};
-        GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - j - 1)));
+        GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - j - 1), s1));
       }
     }
-    if (Jend < nt) {
-      const long t = nt - Jend;
-      SyrkPolicy p{A, ld, 1, Jend, J0 * NB, Jend * NB};
-      GPRC_CHECK(launch_gemm(ctx, p, dim3((unsigned)(t * (t + 1) / 2))));
+    GPRC_CUDA(cudaEventRecord(ctx->ev_panel, s1));
+    return 0;
+  };
+
+  GPRC_CHECK(panel(0, nt < OUTER_BLOCKS ? nt : OUTER_BLOCKS));
+  for (int J0 = 0; J0 < nt; J0 += OUTER_BLOCKS) {
+    const int Jend = (J0 + OUTER_BLOCKS < nt) ? J0 + OUTER_BLOCKS : nt;
+    if (Jend >= nt) break;
+    const int Nend = (Jend + OUTER_BLOCKS < nt) ? Jend + OUTER_BLOCKS : nt;
+    // LA(P): columns of the next panel, on the panel stream, after rest(P - 1) has finished with them
+    if (J0 > 0) GPRC_CUDA(cudaStreamWaitEvent(s1, ctx->ev_rest, 0));
+    for (int tj = Jend; tj < Nend; ++tj) {
+      SyrkPolicy p{A, ld, 0, tj, J0 * NB, Jend * NB};
+      GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - tj), s1));
     }
+    // rest(P): everything right of the next panel, on the main stream, once panel P is factored
+    GPRC_CUDA(cudaStreamWaitEvent(s0, ctx->ev_panel, 0));
+    if (Nend < nt) {
+      const long t = nt - Nend;
+      SyrkPolicy p{A, ld, 1, Nend, J0 * NB, Jend * NB};
+      GPRC_CHECK(launch_gemm(ctx, p, dim3((unsigned)(t * (t + 1) / 2)), s0));
+    }
+    GPRC_CUDA(cudaEventRecord(ctx->ev_rest, s0));
+    GPRC_CHECK(panel(Jend, Nend));
   }
+  GPRC_CUDA(cudaStreamWaitEvent(s0, ctx->ev_panel, 0));
   return 0;
 }
 
-// copy the inverted diagonal blocks into the diagonal tiles of W (full tiles incl. the explicit zeros)
-__global__ void place_diag_blocks_kernel(const double* __restrict__ dinv, double* __restrict__ W, long ld) {
+// copy the inverted diagonal blocks into the diagonal tiles of W, and their transposes into those of Wt
+__global__ void place_diag_blocks_kernel(const double* __restrict__ dinv, double* __restrict__ W,
+                                         double* __restrict__ Wt, long ld) {
   const int j = blockIdx.x;
   const double* src = dinv + (long)j * NB * NB;
   double* dst = W + (long)j * NB * (ld + 1);
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(e & (NB - 1)) + (long)(e >> 7) * ld] = src[e];
+  double* dstt = Wt + (long)j * NB * (ld + 1);
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e & (NB - 1), c = e >> 7;
+    dst[r + (long)c * ld] = src[e];
+    dstt[r + (long)c * ld] = src[c + r * NB];
+  }
 }
 
 // W = L^-1 (lower), level by level (see Trtri1Policy).  S: n x n scratch (only block positions strictly above the
-// diagonal are written, so S may alias the buffer holding L).
-inline int trtri_levels(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, double* W, double* S) {
+// diagonal are written, so S may alias the buffer holding L).  Wt: n x n, receives W^T (needed only during the
+// inversion; the caller may free it afterwards).
+inline int trtri_levels(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, double* W, double* Wt,
+                        double* S) {
   const int nt = (int)(n / NB);
-  place_diag_blocks_kernel<<<nt, 256, 0, ctx->stream>>>(dinv, W, ld);
+  place_diag_blocks_kernel<<<nt, 256, 0, ctx->stream>>>(dinv, W, Wt, ld);
   ctx->launches++;
   GPRC_CUDA(cudaGetLastError());
   for (int s = 1; s < nt; s *= 2) {
     const int groups = (nt + 2 * s - 1) / (2 * s);
-    Trtri1Policy p1{L, W, S, ld, s, nt};
+    Trtri1Policy p1{L, Wt, S, ld, s, nt};
     GPRC_CHECK(launch_gemm(ctx, p1, dim3(s, s, groups)));
-    Trtri2Policy p2{W, S, ld, s, nt};
+    Trtri2Policy p2{W, Wt, S, ld, s, nt};
     GPRC_CHECK(launch_gemm(ctx, p2, dim3(s, s, groups)));
   }
   return 0;
