@@ -500,7 +500,7 @@ def vmmin(b0, fminfn, fmingr, maxit=100, abstol=-math.inf, reltol=math.sqrt(EPS)
                     D2 = 1.0 + D2 / D1
                     for i in range(n):
                         for j in range(i + 1):
-                            B[i, j] += (D2 * t[i] * t[j] - X[i] * c[j] - t[i] * X[j]) / D1
+                            B[i, j] += (D2 * t[i] * t[j] - X[i] * t[j] - t[i] * X[j]) / D1
                 else:
                     ilast = gradcount
             else:
