@@ -1,0 +1,31 @@
+#' gprc: Gaussian-process regression and classification on the GPU
+#'
+#' Same exported API as the CPU package (GPR, GPC, fit, cov_func, iid_noise, simulate_*); the numerical hot path
+#' (kernel-matrix build, Cholesky, triangular solves, Laplace Newton loop) runs in libgprc through `.Call`.
+#' Device selection: options(gprc.device = 0L).  There is no CPU fallback.
+#'
+#' @useDynLib gprc, .registration = TRUE
+#' @importFrom R6 R6Class
+"_PACKAGE"
+
+# ---- kernel descriptors ------------------------------------------------------------------------------------------
+# A closure made by cov_func()/fit() carries attr(k, "gprc_kernel") = list(id=, <named parameters>); GPR/GPC hand such
+# kernels to the device.  Any other function(x, y) is evaluated in R exactly as before (covariance_matrix via outer)
+# and only the factorisation / solves run on the device ("precomputed" entry points).
+.gprc_ids <- c(constant = 0L, linear = 1L, polynomial = 2L, sqrexp = 3L, gammaexp = 4L, rationalquadratic = 5L)
+
+.gprc_tag <- function(closure, func, args) {
+  for (nm in names(.gprc_ids)) {
+    if (identical(func, get(nm, envir = asNamespace("gprc")))) {
+      formal <- setdiff(names(formals(get(paste0(nm, ".matrix"), envir = asNamespace("gprc")))), c("x", "y"))
+      if (is.null(names(args))) names(args) <- rep("", length(args))
+      unnamed <- which(names(args) == "")
+      names(args)[unnamed] <- setdiff(formal, names(args))[seq_along(unnamed)]
+      if (setequal(names(args), formal))
+        attr(closure, "gprc_kernel") <- c(list(id = .gprc_ids[[nm]]), lapply(args[formal], as.double))
+    }
+  }
+  closure
+}
+
+.gprc_spec <- function(k) attr(k, "gprc_kernel", exact = TRUE)

@@ -21,9 +21,13 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
   if (tid < NB) bj[tid] = b[(long)j * NB + tid];
   __syncthreads();
   const double* Li = dinv + (long)j * NB * NB;
-  double s = 0.0;
-#pragma unroll 8
-  for (int c = h * 64; c < h * 64 + 64; ++c) s = fma(Li[r + c * NB], bj[c], s);  // explicit zeros above the diagonal
+  double s = 0.0, s2 = 0.0;
+#pragma unroll 16
+  for (int c = h * 64; c < h * 64 + 64; c += 2) {  // explicit zeros above the diagonal
+    s = fma(Li[r + c * NB], bj[c], s);
+    s2 = fma(Li[r + (c + 1) * NB], bj[c + 1], s2);
+  }
+  s += s2;
   if (h == 1) part[r] = s;
   __syncthreads();
   if (h == 0) xj[r] = s + part[r];
@@ -35,10 +39,13 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
     const long row = row0 + q * 256 + tid;
     if (row < n) {
       const double* Lp = L + row + (long)j * NB * ld;
-      double acc = 0.0;
+      double acc = 0.0, acc2 = 0.0;
 #pragma unroll 16
-      for (int c = 0; c < NB; ++c) acc = fma(Lp[(long)c * ld], xj[c], acc);
-      b[row] -= acc;
+      for (int c = 0; c < NB; c += 2) {
+        acc = fma(Lp[(long)c * ld], xj[c], acc);
+        acc2 = fma(Lp[(long)(c + 1) * ld], xj[c + 1], acc2);
+      }
+      b[row] -= acc + acc2;
     }
   }
 }
@@ -54,32 +61,47 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __rest
   if (tid < NB) bj[tid] = b[(long)j * NB + tid];
   __syncthreads();
   const double* Li = dinv + (long)j * NB * NB;
-  for (int r = warp; r < NB; r += 8) {  // x_j[r] = sum_{c >= r} Linv[c, r] b_j[c]
-    double s = 0.0;
+  {
+    // x_j[r] = sum_{c >= r} Linv[c, r] b_j[c]: each warp owns 16 rows; all 64 loads of a lane are independent
+    double s[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = lane + 32 * q;
-      s = fma(Li[c + r * NB], bj[c], s);
+    for (int rr = 0; rr < 16; ++rr) {
+      const int r = warp + 8 * rr;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = lane + 32 * q;
+        acc = fma(Li[c + r * NB], bj[c], acc);
+      }
+      s[rr] = acc;
     }
-    s = warp_sum(s);
-    if (lane == 0) xj[r] = s;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const double t = warp_sum(s[rr]);
+      if (lane == 0) xj[warp + 8 * rr] = t;
+    }
   }
   __syncthreads();
   if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
   if ((int)blockIdx.x >= j) return;         // j == 0: nothing left to update
   const long col0 = (long)blockIdx.x * NB;  // this CTA updates columns [col0, col0 + 128), all < j * 128
   const double* Lrow = L + (long)j * NB;
-  for (int kk = warp; kk < NB; kk += 8) {
-    const long k = col0 + kk;
-    const double* Lp = Lrow + k * ld;
-    double s = 0.0;
+  double xr[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = lane + 32 * q;
-      s = fma(Lp[c], xj[c], s);
-    }
-    s = warp_sum(s);
-    if (lane == 0) b[k] -= s;
+  for (int q = 0; q < 4; ++q) xr[q] = xj[lane + 32 * q];
+  double s[16];
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const double* Lp = Lrow + (col0 + warp + 8 * kk) * ld;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc = fma(Lp[lane + 32 * q], xr[q], acc);
+    s[kk] = acc;
+  }
+#pragma unroll
+  for (int kk = 0; kk < 16; ++kk) {
+    const double t = warp_sum(s[kk]);
+    if (lane == 0) b[col0 + warp + 8 * kk] -= t;
   }
 }
 

@@ -1,0 +1,42 @@
+/* Minimal stand-in for R's C API: just enough declarations to compile-check src/gprc_shim.c where R is not
+ * installed.  It defines no behaviour; the real build uses R's own headers. */
+#ifndef STUB_RINTERNALS_H
+#define STUB_RINTERNALS_H
+#include <stddef.h>
+typedef struct SEXPREC* SEXP;
+typedef ptrdiff_t R_xlen_t;
+typedef enum { FALSE = 0, TRUE } Rboolean;
+#define REALSXP 14
+#define VECSXP 19
+extern SEXP R_NilValue, R_NamesSymbol;
+extern double R_NaReal;
+#define NA_REAL R_NaReal
+double* REAL(SEXP);
+R_xlen_t XLENGTH(SEXP);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
+SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+SEXP STRING_ELT(SEXP, R_xlen_t);
+const char* CHAR(SEXP);
+SEXP Rf_getAttrib(SEXP, SEXP);
+SEXP Rf_install(const char*);
+SEXP Rf_GetOption1(SEXP);
+int Rf_asInteger(SEXP);
+int Rf_asLogical(SEXP);
+double Rf_asReal(SEXP);
+int Rf_nrows(SEXP);
+int Rf_ncols(SEXP);
+SEXP Rf_allocVector(unsigned int, R_xlen_t);
+SEXP Rf_allocMatrix(unsigned int, int, int);
+SEXP Rf_ScalarReal(double);
+SEXP Rf_ScalarInteger(int);
+SEXP Rf_protect(SEXP);
+void Rf_unprotect(int);
+#define PROTECT(s) Rf_protect(s)
+#define UNPROTECT(n) Rf_unprotect(n)
+void Rf_error(const char*, ...) __attribute__((noreturn));
+SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
+void* R_ExternalPtrAddr(SEXP);
+void R_ClearExternalPtr(SEXP);
+typedef void (*R_CFinalizer_t)(SEXP);
+void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
+#endif
