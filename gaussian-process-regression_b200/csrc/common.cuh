@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gprc.h"
@@ -75,6 +77,11 @@ struct gprc_ctx {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t marks[8] = {nullptr};
+  // caching device allocator: fit()/predict allocate n^2-sized buffers on every call (an optimiser calls gprc_logml
+  // hundreds of times) and cudaMalloc/cudaFree are slow and synchronising; freed blocks are kept for reuse
+  std::multimap<size_t, void*> pool_free;
+  std::unordered_map<void*, size_t> pool_live;
+  size_t pool_cached_bytes = 0;
   long* d_info = nullptr;     // device scratch for LAPACK-style info
   double* d_scalars = nullptr;  // device scratch for small reductions (64 doubles)
   double* h_scalars = nullptr;  // pinned mirror

@@ -16,28 +16,76 @@ thread_local std::string g_last_error;
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
+static thread_local gprc_ctx* tl_ctx = nullptr;  // context of the API call in flight (routes dmalloc/dfree to its pool)
+
 struct DeviceGuard {
   int prev = -1;
-  explicit DeviceGuard(int dev) {
+  gprc_ctx* prev_ctx = nullptr;
+  explicit DeviceGuard(gprc_ctx* c) {
     cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
+    if (prev != c->device) cudaSetDevice(c->device);
+    prev_ctx = tl_ctx;
+    tl_ctx = c;
   }
   ~DeviceGuard() {
     int cur;
     cudaGetDevice(&cur);
     if (cur != prev && prev >= 0) cudaSetDevice(prev);
+    tl_ctx = prev_ctx;
   }
 };
+
+static void pool_trim(gprc_ctx* c) {
+  for (auto& kv : c->pool_free) cudaFree(kv.second);
+  c->pool_free.clear();
+  c->pool_cached_bytes = 0;
+}
+
+static int pool_alloc(gprc_ctx* c, void** p, size_t bytes) {
+  const size_t gran = 2u << 20;
+  bytes = (bytes + gran - 1) / gran * gran;
+  auto it = c->pool_free.lower_bound(bytes);
+  if (it != c->pool_free.end() && it->first <= bytes + bytes / 4) {  // reuse a cached block of (nearly) this size
+    *p = it->second;
+    c->pool_cached_bytes -= it->first;
+    c->pool_live[*p] = it->first;
+    c->pool_free.erase(it);
+    return 0;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {  // out of memory: give the cache back and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(c->stream);
+    pool_trim(c);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) return set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  c->pool_live[*p] = bytes;
+  return 0;
+}
 
 template <class T>
 static int dmalloc(T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
+  if (tl_ctx) return pool_alloc(tl_ctx, reinterpret_cast<void**>(p), count * sizeof(T));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
   return 0;
 }
+// Returned blocks may still be in use by kernels queued on the context's streams; they are only handed out again to
+// work queued on the same streams, so stream order keeps that safe.
 static void dfree(void* p) {
-  if (p) cudaFree(p);
+  if (!p) return;
+  if (tl_ctx) {
+    auto it = tl_ctx->pool_live.find(p);
+    if (it != tl_ctx->pool_live.end()) {
+      tl_ctx->pool_free.emplace(it->second, p);
+      tl_ctx->pool_cached_bytes += it->second;
+      tl_ctx->pool_live.erase(it);
+      return;
+    }
+  }
+  cudaFree(p);
 }
 
 // kernel spec: host struct -> device struct (sigma_vec uploaded, owned by the caller of make_spec)
@@ -256,7 +304,7 @@ extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
 
 extern "C" void gprc_ctx_free(gprc_ctx* c) {
   if (!c) return;
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   cudaStreamSynchronize(c->stream);
   for (auto& p : c->pending) {
     cudaEventDestroy(p.a);
@@ -265,6 +313,9 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
   for (auto e : c->event_pool) cudaEventDestroy(e);
   for (auto e : c->marks)
     if (e) cudaEventDestroy(e);
+  pool_trim(c);
+  for (auto& kv : c->pool_live) cudaFree(kv.first);
+  c->pool_live.clear();
   cudaFree(c->d_info);
   cudaFree(c->d_scalars);
   cudaFreeHost(c->h_scalars);
@@ -289,7 +340,7 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
 
 extern "C" int gprc_ctx_sync(gprc_ctx* c) {
   GPRC_ARG(c != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -306,7 +357,7 @@ static void resolve_timers(gprc_ctx* c) {
 
 extern "C" void gprc_ctx_reset_timers(gprc_ctx* c) {
   if (!c) return;
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   cudaStreamSynchronize(c->stream);
   resolve_timers(c);
   for (int i = 0; i < GPRC_T_COUNT; ++i) c->timers[i] = 0.0;
@@ -315,7 +366,7 @@ extern "C" void gprc_ctx_reset_timers(gprc_ctx* c) {
 
 extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
   GPRC_ARG(c != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaStreamSynchronize(c->stream));
   resolve_timers(c);
   if (ms)
@@ -326,14 +377,14 @@ extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
 
 extern "C" int gprc_ctx_mark(gprc_ctx* c, int slot) {
   GPRC_ARG(c != nullptr && slot >= 0 && slot < 8);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   if (!c->marks[slot]) GPRC_CUDA(cudaEventCreate(&c->marks[slot]));
   GPRC_CUDA(cudaEventRecord(c->marks[slot], c->stream));
   return 0;
 }
 extern "C" int gprc_ctx_elapsed_ms(gprc_ctx* c, int a, int b, double* ms) {
   GPRC_ARG(c != nullptr && ms != nullptr && a >= 0 && a < 8 && b >= 0 && b < 8 && c->marks[a] && c->marks[b]);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaEventSynchronize(c->marks[b]));
   float f = 0.f;
   GPRC_CUDA(cudaEventElapsedTime(&f, c->marks[a], c->marks[b]));
@@ -344,27 +395,27 @@ extern "C" int gprc_ctx_elapsed_ms(gprc_ctx* c, int a, int b, double* ms) {
 // ---- device memory helpers --------------------------------------------------------------------------------------
 extern "C" int gprc_dev_malloc(gprc_ctx* c, void** dptr, unsigned long long bytes) {
   GPRC_ARG(c != nullptr && dptr != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
   return 0;
 }
 extern "C" int gprc_dev_free(gprc_ctx* c, void* dptr) {
   GPRC_ARG(c != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaStreamSynchronize(c->stream));
   GPRC_CUDA(cudaFree(dptr));
   return 0;
 }
 extern "C" int gprc_dev_h2d(gprc_ctx* c, void* dptr, const void* host, unsigned long long bytes) {
   GPRC_ARG(c != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
   GPRC_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 extern "C" int gprc_dev_d2h(gprc_ctx* c, void* host, const void* dptr, unsigned long long bytes) {
   GPRC_ARG(c != nullptr);
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   GPRC_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
   GPRC_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
@@ -414,7 +465,7 @@ extern "C" int gprc_cov_matrix(gprc_ctx* c, const gprc_kernel* k, const double* 
                                long nB, double* out) {
   GPRC_ARG(c && k && A && B && out && d > 0 && nA >= 0 && nB >= 0);
   if (nA == 0 || nB == 0) return 0;
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   SpecHolder spec;
   GPRC_CHECK(make_spec(c, k, d, spec));
   double *dA = nullptr, *dB = nullptr, *dout = nullptr;
@@ -454,7 +505,7 @@ extern "C" int gprc_cov_pointwise(gprc_ctx* c, const gprc_kernel* k, const doubl
                                   double* out) {
   GPRC_ARG(c && k && A && B && out && d > 0 && n >= 0);
   if (n == 0) return 0;
-  DeviceGuard g(c->device);
+  DeviceGuard g(c);
   SpecHolder spec;
   GPRC_CHECK(make_spec(c, k, d, spec));
   double *dA = nullptr, *dB = nullptr, *dout = nullptr;
@@ -507,14 +558,16 @@ static int factor_run(gprc_ctx* c, FactorState& F, long* info) {
 static int ensure_inverse(gprc_ctx* c, FactorState& F) {
   if (F.W) return 0;
   GPRC_CHECK(dmalloc(&F.W, (size_t)F.n_pad * F.n_pad));
-  PhaseTimer t(c, GPRC_T_TRTRI);
-  GPRC_CUDA(cudaMemsetAsync(F.W, 0, sizeof(double) * F.n_pad * F.n_pad, c->stream));  // zeros above the diagonal
   // scratch for the level products aliases the (unused) strictly upper block triangle of the L buffer;
   // W^T is only needed while inverting
   double* Wt = nullptr;
   GPRC_CHECK(dmalloc(&Wt, (size_t)F.n_pad * F.n_pad));
-  int rc = trtri_levels(c, F.L, F.n_pad, F.n_pad, F.dinv, F.W, Wt, F.L);
-  cudaStreamSynchronize(c->stream);
+  int rc;
+  {
+    PhaseTimer t(c, GPRC_T_TRTRI);
+    GPRC_CUDA(cudaMemsetAsync(F.W, 0, sizeof(double) * F.n_pad * F.n_pad, c->stream));  // zeros above the diagonal
+    rc = trtri_levels(c, F.L, F.n_pad, F.n_pad, F.dinv, F.W, Wt, F.L);
+  }
   dfree(Wt);
   return rc;
 }
@@ -719,7 +772,7 @@ static int gpr_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, bo
   GPRC_ARG(Kpre != nullptr || (k != nullptr && X != nullptr && d > 0));
   *out = nullptr;
   *info = 0;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   gprc_gpr* g = new gprc_gpr();
   g->ctx = c;
   g->d = d;
@@ -779,7 +832,7 @@ extern "C" int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, doub
   GPRC_ARG(g && dXs && dmean && dvar && m >= 0);
   GPRC_ARG(!g->precomputed);
   if (m == 0) return 0;
-  DeviceGuard guard(g->ctx->device);
+  DeviceGuard guard(g->ctx);
   return predict_pointwise_dev(g->ctx, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar);
 }
 
@@ -788,7 +841,7 @@ extern "C" int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* m
   GPRC_ARG(!g->precomputed);
   if (m == 0) return 0;
   gprc_ctx* c = g->ctx;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   double *dXs = nullptr, *dmean = nullptr, *dvar = nullptr;
   int rc = 0;
   do {
@@ -813,7 +866,7 @@ extern "C" int gprc_gpr_predict_precomputed(gprc_gpr* g, const double* Ks, const
                                             double* var) {
   GPRC_ARG(g && Ks && kss && mean && var && m >= 0);
   if (m == 0) return 0;
-  DeviceGuard guard(g->ctx->device);
+  DeviceGuard guard(g->ctx);
   return predict_precomputed(g->ctx, g->F, g->ws, g->alpha, nullptr, Ks, kss, m, mean, var);
 }
 
@@ -822,7 +875,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
   GPRC_ARG(g && Xs && mean && cov && m > 0);
   GPRC_ARG(!g->precomputed);
   gprc_ctx* c = g->ctx;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   FactorState& F = g->F;
   const long mp = round_up(m, NB);
   GPRC_CHECK(ensure_inverse(c, F));
@@ -888,7 +941,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
 extern "C" int gprc_gpr_get(gprc_gpr* g, int what, double* host) {
   GPRC_ARG(g && host);
   gprc_ctx* c = g->ctx;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   switch (what) {
     case GPRC_GET_L: return download_lower(c, g->F.L, g->F.n, g->F.n_pad, host);
     case GPRC_GET_LINV:
@@ -901,7 +954,7 @@ extern "C" int gprc_gpr_get(gprc_gpr* g, int what, double* host) {
 extern "C" long gprc_gpr_n(const gprc_gpr* g) { return g ? g->F.n : 0; }
 extern "C" void gprc_gpr_free(gprc_gpr* g) {
   if (!g) return;
-  DeviceGuard guard(g->ctx->device);
+  DeviceGuard guard(g->ctx);
   cudaStreamSynchronize(g->ctx->stream);
   gpr_destroy(g);
 }
@@ -921,7 +974,7 @@ extern "C" int gprc_logml(gprc_ctx* c, const gprc_kernel* k, const double* X, in
 extern "C" int gprc_logml_batch(gprc_ctx* c, const gprc_kernel* specs, int nspec, const double* X, int d, long n,
                                 const double* y, double noise, double* logp, double* min_leading_logdet, long* info) {
   GPRC_ARG(c && specs && nspec >= 0 && X && y && logp && info && n > 0 && d > 0);
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   // X and y are uploaded once; every evaluation reuses them on the device
   double *dX = nullptr, *dy = nullptr;
   int rc = 0;
@@ -1073,7 +1126,7 @@ extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* 
   GPRC_CHECK(gpr_fit_common(c, k, X, false, d, n, y, false, nullptr, textbook ? noise : 0.0, &g, nullptr, info,
                             nullptr));
   if (*info != 0 || !g) return 0;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   FactorState& F = g->F;
   const long np = F.n_pad;
   double *dK0 = nullptr, *dK1 = nullptr, *vec = nullptr, *ones = nullptr, *Z = nullptr;
@@ -1152,7 +1205,7 @@ static int gpc_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, in
   *out = nullptr;
   *iters = 0;
   *status = 0;
-  DeviceGuard dg(c->device);
+  DeviceGuard dg(c);
   gprc_gpc* g = new gprc_gpc();
   g->ctx = c;
   g->d = d;
@@ -1301,7 +1354,7 @@ extern "C" int gprc_gpc_predict_latent(gprc_gpc* g, const double* Xs, long m, do
   GPRC_ARG(!g->precomputed);
   if (m == 0) return 0;
   gprc_ctx* c = g->ctx;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   double *dXs = nullptr, *dmean = nullptr, *dvar = nullptr;
   int rc = 0;
   do {
@@ -1325,13 +1378,13 @@ extern "C" int gprc_gpc_predict_latent_precomputed(gprc_gpc* g, const double* Ks
                                                    double* fs_bar, double* Vfs) {
   GPRC_ARG(g && Ks && kss && fs_bar && Vfs && m >= 0);
   if (m == 0) return 0;
-  DeviceGuard guard(g->ctx->device);
+  DeviceGuard guard(g->ctx);
   return predict_precomputed(g->ctx, g->F, g->ws, g->gradl, g->sw, Ks, kss, m, fs_bar, Vfs);
 }
 extern "C" int gprc_gpc_get(gprc_gpc* g, int what, double* host) {
   GPRC_ARG(g && host);
   gprc_ctx* c = g->ctx;
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   switch (what) {
     case GPRC_GET_L: return download_lower(c, g->F.L, g->F.n, g->F.n_pad, host);
     case GPRC_GET_FHAT: return gprc_dev_d2h(c, host, g->f, sizeof(double) * g->F.n);
@@ -1342,7 +1395,7 @@ extern "C" int gprc_gpc_get(gprc_gpc* g, int what, double* host) {
 extern "C" long gprc_gpc_n(const gprc_gpc* g) { return g ? g->F.n : 0; }
 extern "C" void gprc_gpc_free(gprc_gpc* g) {
   if (!g) return;
-  DeviceGuard guard(g->ctx->device);
+  DeviceGuard guard(g->ctx);
   cudaStreamSynchronize(g->ctx->stream);
   gpc_destroy(g);
 }
@@ -1352,7 +1405,7 @@ extern "C" void gprc_gpc_free(gprc_gpc* g) {
 // =================================================================================================================
 extern "C" int gprc_dev_potrf(gprc_ctx* c, double* dA, long n, long ld, double* dinv, long* info) {
   GPRC_ARG(c && dA && dinv && info && n > 0 && n % NB == 0 && ld % NB == 0 && ld >= n);
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   *c->h_info = LONG_MAX;
   GPRC_CUDA(cudaMemcpyAsync(c->d_info, c->h_info, sizeof(long), cudaMemcpyHostToDevice, c->stream));
   {
@@ -1369,7 +1422,7 @@ extern "C" int gprc_dev_dgemm(gprc_ctx* c, int transb, long M, long N, long K, d
                               const double* dB, long ldb, double beta, double* dC, long ldc) {
   GPRC_ARG(c && dA && dB && dC && M > 0 && N > 0 && K >= 0);
   GPRC_ARG(M % NB == 0 && N % NB == 0 && K % BK == 0 && lda % 2 == 0 && ldb % 2 == 0);
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   const dim3 grid((unsigned)((M / NB) * (N / NB)));
   if (transb) {
     DgemmPolicy<false> p{dA, lda, dB, ldb, dC, ldc, alpha, beta, (int)K, (int)(M / NB)};
@@ -1382,7 +1435,7 @@ extern "C" int gprc_dev_dgemm(gprc_ctx* c, int transb, long M, long N, long K, d
 extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, const double* dinv, double* dW,
                               double* dscratch) {
   GPRC_ARG(c && dL && dinv && dW && dscratch && n > 0 && n % NB == 0 && ld % NB == 0 && ld >= n);
-  DeviceGuard guard(c->device);
+  DeviceGuard guard(c);
   double* Wt = nullptr;
   GPRC_CHECK(dmalloc(&Wt, (size_t)n * ld));
   int rc;
