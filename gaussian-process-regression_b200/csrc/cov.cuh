@@ -70,6 +70,7 @@ struct CovParams {
   // the same two fusions along the other axis (K_star^T builds: rows are test points, columns training points)
   const double* colscale;    // nullable: stored value is colscale[j] * k
   const double* colweights;  // nullable: pmean[tile_j][i] = sum_{j in tile} k(i, j) * colweights[j]
+  long col_offset;           // column j of this call is column j + col_offset of the full matrix (panel builds)
 };
 
 constexpr int CT = 64;    // covariance tile
@@ -79,7 +80,7 @@ template <int FAMILY>
 __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const long ti = blockIdx.x, tj = blockIdx.y;
-  if (p.lower_only && tj > ti) return;
+  if (p.lower_only && tj * CT + p.col_offset > ti * CT + (CT - 1)) return;
   __shared__ double sh[2 * CDCH * (CT + 1)];  // one array: the row-sum reduction below reuses all of it
   double (*As)[CT + 1] = reinterpret_cast<double (*)[CT + 1]>(sh);
   double (*Bs)[CT + 1] = reinterpret_cast<double (*)[CT + 1]>(sh + CDCH * (CT + 1));
@@ -141,13 +142,13 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
       double v;
       if (gi < p.nA && gj < p.nB) {
         v = (FAMILY == FAM_DIST) ? kfun_dist(p.k, acc[qa][qb]) : (FAMILY == FAM_DOT) ? kfun_dot(p.k, acc[qa][qb]) : p.k.c;
-        if (p.symmetric && gi == gj) v += p.diag_add;
+        if (p.symmetric && gi == gj + p.col_offset) v += p.diag_add;
         if (p.weights) msum[qb] = fma(v, p.weights[gi], msum[qb]);
         if (p.colweights) rsum[qa] = fma(v, p.colweights[gj], rsum[qa]);
         if (p.rowscale) v *= p.rowscale[gi];
         if (p.colscale) v *= p.colscale[gj];
       } else {
-        v = (p.pad_identity && gi == gj) ? 1.0 : 0.0;
+        v = (p.pad_identity && gi == gj + p.col_offset) ? 1.0 : 0.0;
       }
       if (gi < p.rows_pad && gj < p.cols_pad) p.out[gi + gj * p.ldo] = v;
     }

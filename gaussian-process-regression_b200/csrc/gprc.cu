@@ -458,6 +458,7 @@ static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d
   p.ldpm = ldpm;
   p.colscale = colscale;
   p.colweights = colweights;
+  p.col_offset = 0;
   return launch_cov(c, p);
 }
 
@@ -1445,5 +1446,309 @@ extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, co
   }
   cudaStreamSynchronize(c->stream);
   dfree(Wt);
+  return rc;
+}
+
+// =================================================================================================================
+// multi-GPU Cholesky + solve (dist.cuh)
+// =================================================================================================================
+#include "dist.cuh"
+
+extern "C" int gprc_dist_unique_id(char* id128, const char* nccl_path) {
+  GPRC_ARG(id128 != nullptr);
+  static NcclApi api;
+  GPRC_CHECK(nccl_load(api, nccl_path));
+  ncclUniqueId id;
+  GPRC_NCCL(api, api.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+extern "C" int gprc_dist_create(gprc_ctx* c, const char* id128, int rank, int world, const char* nccl_path,
+                                gprc_dist** out) {
+  GPRC_ARG(c && id128 && out && world >= 1 && rank >= 0 && rank < world);
+  *out = nullptr;
+  DeviceGuard guard(c);
+  gprc_dist* D = new gprc_dist();
+  D->ctx = c;
+  D->rank = rank;
+  D->world = world;
+  int rc = nccl_load(D->api, nccl_path);
+  if (rc) {
+    delete D;
+    return rc;
+  }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = D->api.CommInitRank(&D->comm, world, id, rank);
+  if (r != ncclSuccess) {
+    set_error(-5, __FILE__, __LINE__, D->api.GetErrorString(r));
+    delete D;
+    return -5;
+  }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  GPRC_CUDA(cudaStreamCreateWithPriority(&D->s_comm, cudaStreamNonBlocking, hi));
+  GPRC_CUDA(cudaEventCreateWithFlags(&D->ev_packed, cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&D->ev_bcast[0], cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&D->ev_bcast[1], cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&D->ev_rest, cudaEventDisableTiming));
+  GPRC_CUDA(cudaEventCreateWithFlags(&D->ev_begin, cudaEventDisableTiming));
+  *out = D;
+  return 0;
+}
+
+extern "C" void gprc_dist_free(gprc_dist* D) {
+  if (!D) return;
+  DeviceGuard guard(D->ctx);
+  cudaStreamSynchronize(D->s_comm);
+  cudaStreamSynchronize(D->ctx->stream);
+  if (D->comm) D->api.CommDestroy(D->comm);
+  cudaEventDestroy(D->ev_packed);
+  cudaEventDestroy(D->ev_bcast[0]);
+  cudaEventDestroy(D->ev_bcast[1]);
+  cudaEventDestroy(D->ev_rest);
+  cudaEventDestroy(D->ev_begin);
+  cudaStreamDestroy(D->s_comm);
+  delete D;
+}
+
+extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                                 double noise, double* logp, double* alpha, long* info, double* phase_ms) {
+  GPRC_ARG(D && k && X && y && logp && info && n > 0 && d > 0 && noise >= 0.0);
+  gprc_ctx* c = D->ctx;
+  DeviceGuard guard(c);
+  NcclApi& api = D->api;
+  const int N = D->world, me = D->rank;
+  const long n_pad = round_up(n, PANEL);
+  const int npan = (int)(n_pad / PANEL), nt = (int)(n_pad / NB);
+  const int nown = (npan - me + N - 1) / N;  // panels me, me + N, ...
+  const long slab = n_pad * PANEL;
+  cudaStream_t s0 = c->stream, s1 = c->stream_hi, sc = D->s_comm;
+  static bool configured[64] = {false};
+  if (!configured[c->device & 63]) {
+    GPRC_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM_BYTES));
+    configured[c->device & 63] = true;
+  }
+  SpecHolder spec;
+  GPRC_CHECK(make_spec(c, k, d, spec));
+  double *dX = nullptr, *Aloc = nullptr, *dinv = nullptr, *diag = nullptr, *Pbuf[2] = {nullptr, nullptr}, *vec = nullptr,
+         *dy = nullptr, *partial = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+  int rc = 0;
+  *info = 0;
+  do {
+    if ((rc = dmalloc(&dX, (size_t)d * n)) || (rc = dmalloc(&Aloc, (size_t)std::max(nown, 1) * slab)) ||
+        (rc = dmalloc(&dinv, (size_t)n_pad * NB)) || (rc = dmalloc(&diag, (size_t)n_pad)) ||
+        (rc = dmalloc(&Pbuf[0], (size_t)slab)) || (rc = dmalloc(&Pbuf[1], (size_t)slab)) ||
+        (rc = dmalloc(&vec, (size_t)2 * n_pad)) || (rc = dmalloc(&dy, (size_t)n_pad)) ||
+        (rc = dmalloc(&partial, (size_t)((n_pad + BWD_CHUNK - 1) / BWD_CHUNK) * NB)))
+      break;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    cudaEventCreate(&e3);
+    cudaMemcpyAsync(dX, X, sizeof(double) * d * n, cudaMemcpyHostToDevice, s0);
+    cudaMemsetAsync(dy, 0, sizeof(double) * n_pad, s0);
+    cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, s0);
+    cudaMemsetAsync(diag, 0, sizeof(double) * n_pad, s0);
+    *c->h_info = LONG_MAX;
+    cudaMemcpyAsync(c->d_info, c->h_info, sizeof(long), cudaMemcpyHostToDevice, s0);
+    cudaEventRecord(e0, s0);
+    // ---- build the owned panels of K + noise I (lower part, identity padding) ----
+    for (int q = 0; q < nown && rc == 0; ++q) {
+      const long p = me + (long)q * N, c0 = p * PANEL;
+      CovParams cp;
+      cp.k = spec.dev;
+      cp.A = dX;
+      cp.B = dX + c0 * d;
+      cp.d = d;
+      cp.nA = n;
+      cp.nB = std::max<long>(0, std::min<long>(PANEL, n - c0));
+      cp.out = Aloc + q * slab;
+      cp.ldo = n_pad;
+      cp.rows_pad = n_pad;
+      cp.cols_pad = PANEL;
+      cp.lower_only = 1;
+      cp.symmetric = 1;
+      cp.diag_add = noise;
+      cp.pad_identity = 1;
+      cp.rowscale = cp.weights = nullptr;
+      cp.pmean = nullptr;
+      cp.ldpm = 0;
+      cp.colscale = cp.colweights = nullptr;
+      cp.col_offset = c0;
+      rc = launch_cov(c, cp);
+    }
+    if (rc) break;
+    cudaEventRecord(e1, s0);
+
+    // ---- factorisation ----
+    // the single-GPU kernels address the matrix as A[row + col * ld] with GLOBAL indices: give them the slab shifted
+    // left by the panel's first column
+    auto virt = [&](int p) { return Aloc + (long)((p - me) / N) * slab - (long)p * PANEL * n_pad; };
+    auto factor_panel = [&](int p) -> int {
+      double* Av = virt(p);
+      const int J0 = p * OUTER_BLOCKS, Jend = J0 + OUTER_BLOCKS;
+      for (int j = J0; j < Jend; ++j) {
+        if (j > J0) {
+          SyrkPolicy sp{Av, n_pad, 0, j, J0 * NB, j * NB};
+          GPRC_CHECK(launch_gemm(c, sp, dim3(nt - j), s1));
+        }
+        potrf_diag_kernel<<<1, 256, PD_SMEM_BYTES, s1>>>(Av, n_pad, j, dinv + (long)j * NB * NB, c->d_info, diag);
+        c->launches++;
+        if (j + 1 < nt) {
+          TrsmPolicy tp{Av, n_pad, dinv + (long)j * NB * NB, j};
+          GPRC_CHECK(launch_gemm(c, tp, dim3(nt - j - 1), s1));
+        }
+      }
+      // pack rows >= 512 p of the 512 columns into the panel buffer (leading dimension = rows kept)
+      const long rows = n_pad - (long)p * PANEL;
+      GPRC_CUDA(cudaMemcpy2DAsync(Pbuf[p & 1], rows * sizeof(double), Av + (long)p * PANEL * n_pad + (long)p * PANEL,
+                                  n_pad * sizeof(double), rows * sizeof(double), PANEL, cudaMemcpyDeviceToDevice, s1));
+      GPRC_CUDA(cudaEventRecord(D->ev_packed, s1));
+      return 0;
+    };
+    auto update = [&](int p, int first_panel, int count, cudaStream_t st) -> int {
+      if (count <= 0) return 0;
+      DistUpdatePolicy up;
+      up.Aloc = Aloc;
+      up.ld = n_pad;
+      up.slab_elems = slab;
+      up.P = Pbuf[p & 1];
+      up.ldp = n_pad - (long)p * PANEL;
+      up.prow0_tile = p * OUTER_BLOCKS;
+      up.nt = nt;
+      up.q0 = (first_panel - me) / N;
+      up.first_panel = first_panel;
+      up.world = N;
+      long tiles = 0;
+      for (int tj = 0; tj < OUTER_BLOCKS; ++tj) tiles += nt - (first_panel * OUTER_BLOCKS + tj);
+      return launch_gemm(c, up, dim3((unsigned)tiles, (unsigned)count), st);
+    };
+    auto owner = [&](int p) { return p % N; };
+    auto next_owned_after = [&](int p) {  // smallest owned panel index > p
+      int q = p + 1;
+      q += ((me - q) % N + N) % N;
+      return q;
+    };
+
+    GPRC_CUDA(cudaEventRecord(D->ev_begin, s0));
+    GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_begin, 0));
+    GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_begin, 0));
+    if (owner(0) == me) {
+      if ((rc = factor_panel(0))) break;
+      GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
+    }
+    GPRC_NCCL(api, api.Broadcast(Pbuf[0], Pbuf[0], (size_t)n_pad * PANEL, ncclDouble, owner(0), D->comm, sc));
+    GPRC_CUDA(cudaEventRecord(D->ev_bcast[0], sc));
+    for (int p = 0; p < npan && rc == 0; ++p) {
+      const bool own_next = (p + 1 < npan) && owner(p + 1) == me;
+      if (own_next) {
+        // LA: bring panel p + 1 up to date with panel p, then factor it -- all on the high-priority stream
+        GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_bcast[p & 1], 0));
+        if (p > 0) GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_rest, 0));
+        if ((rc = update(p, p + 1, 1, s1))) break;
+        if ((rc = factor_panel(p + 1))) break;
+      }
+      if (p + 1 < npan) {
+        // broadcast of panel p + 1 into the other buffer: it is free once update p - 1 has finished reading it
+        if (p > 0) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_rest, 0));
+        if (own_next) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
+        const long rows = n_pad - (long)(p + 1) * PANEL;
+        GPRC_NCCL(api, api.Broadcast(Pbuf[(p + 1) & 1], Pbuf[(p + 1) & 1], (size_t)rows * PANEL, ncclDouble,
+                                     owner(p + 1), D->comm, sc));
+        GPRC_CUDA(cudaEventRecord(D->ev_bcast[(p + 1) & 1], sc));
+      }
+      // rest(p): every owned panel right of p (and right of p + 1 if that one was just handled by LA)
+      GPRC_CUDA(cudaStreamWaitEvent(s0, D->ev_bcast[p & 1], 0));
+      const int first = next_owned_after(own_next ? p + 1 : p);
+      const int count = (first < npan) ? (npan - 1 - first) / N + 1 : 0;
+      if ((rc = update(p, first, count, s0))) break;
+      GPRC_CUDA(cudaEventRecord(D->ev_rest, s0));
+    }
+    if (rc) break;
+    GPRC_CUDA(cudaStreamWaitEvent(s0, D->ev_packed, 0));
+    GPRC_CUDA(cudaStreamWaitEvent(s0, D->ev_bcast[(npan - 1) & 1], 0));
+    // the diagonal of L lives where its panel lives; the status word is the minimum over ranks
+    GPRC_NCCL(api, api.AllReduce(diag, diag, (size_t)n_pad, ncclDouble, ncclSum, D->comm, s0));
+    GPRC_NCCL(api, api.AllReduce(c->d_info, c->d_info, 1, ncclInt64, ncclMin, D->comm, s0));
+    cudaEventRecord(e2, s0);
+
+    // ---- alpha = L^-T L^-1 y: panels in order, the right-hand side travels by broadcast ----
+    double* bw = vec;           // working right-hand side
+    double* xs = vec + n_pad;   // solution of the current sweep
+    cudaMemcpyAsync(bw, dy, sizeof(double) * n_pad, cudaMemcpyDeviceToDevice, s0);
+    cudaMemsetAsync(xs, 0, sizeof(double) * n_pad, s0);
+    for (int p = 0; p < npan; ++p) {
+      if (owner(p) == me) {
+        double* Av = virt(p);
+        for (int j = p * OUTER_BLOCKS; j < (p + 1) * OUTER_BLOCKS; ++j) {
+          const long below = n_pad - (long)(j + 1) * NB;
+          const unsigned grid = (unsigned)((below + TRSV_ROWS - 1) / TRSV_ROWS);
+          trsv_fwd_step_kernel<<<grid ? grid : 1, 256, 0, s0>>>(Av, n_pad, dinv, j, n_pad, bw, xs);
+          c->launches++;
+        }
+      }
+      GPRC_NCCL(api, api.Broadcast(vec, vec, (size_t)2 * n_pad, ncclDouble, owner(p), D->comm, s0));
+    }
+    cudaMemcpyAsync(bw, xs, sizeof(double) * n_pad, cudaMemcpyDeviceToDevice, s0);  // rhs of L^T x = z
+    cudaMemsetAsync(xs, 0, sizeof(double) * n_pad, s0);
+    for (int p = npan - 1; p >= 0; --p) {
+      if (owner(p) == me) {
+        double* Av = virt(p);
+        for (int j = (p + 1) * OUTER_BLOCKS - 1; j >= p * OUTER_BLOCKS; --j) {
+          const long below = n_pad - (long)(j + 1) * NB;
+          const int parts = (int)((below + BWD_CHUNK - 1) / BWD_CHUNK);
+          if (parts > 0) {
+            trsv_bwd_left_partial_kernel<<<parts, 256, 0, s0>>>(Av, n_pad, j, n_pad, xs, partial);
+            c->launches++;
+          }
+          trsv_bwd_left_diag_kernel<<<1, 256, 0, s0>>>(dinv, j, partial, parts, bw, xs);
+          c->launches++;
+        }
+      }
+      GPRC_NCCL(api, api.Broadcast(xs, xs, (size_t)n_pad, ncclDouble, owner(p), D->comm, s0));
+    }
+    gp_reduce_kernel<<<1, 1024, 0, s0>>>(dy, xs, diag, n, c->d_scalars);
+    c->launches++;
+    cudaEventRecord(e3, s0);
+    cudaMemcpyAsync(c->h_scalars, c->d_scalars, 4 * sizeof(double), cudaMemcpyDeviceToHost, s0);
+    cudaMemcpyAsync(c->h_info, c->d_info, sizeof(long), cudaMemcpyDeviceToHost, s0);
+    if (alpha) cudaMemcpyAsync(alpha, xs, sizeof(double) * n, cudaMemcpyDeviceToHost, s0);
+    cudaError_t e = cudaStreamSynchronize(s0);
+    if (e != cudaSuccess) {
+      rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+      break;
+    }
+    *info = (*c->h_info == LONG_MAX) ? 0 : *c->h_info;
+    *logp = -0.5 * c->h_scalars[0] - c->h_scalars[1] - (double)n / 2.0 * log(2.0 * M_PI);
+    if (phase_ms) {
+      float f = 0.f;
+      cudaEventElapsedTime(&f, e0, e1);
+      phase_ms[0] = f;
+      cudaEventElapsedTime(&f, e1, e2);
+      phase_ms[1] = f;
+      cudaEventElapsedTime(&f, e2, e3);
+      phase_ms[2] = f;
+      cudaEventElapsedTime(&f, e0, e3);
+      phase_ms[3] = f;
+    }
+  } while (0);
+  cudaStreamSynchronize(sc);
+  cudaStreamSynchronize(s1);
+  cudaStreamSynchronize(s0);
+  for (cudaEvent_t ev : {e0, e1, e2, e3})
+    if (ev) cudaEventDestroy(ev);
+  dfree(dX);
+  dfree(Aloc);
+  dfree(dinv);
+  dfree(diag);
+  dfree(Pbuf[0]);
+  dfree(Pbuf[1]);
+  dfree(vec);
+  dfree(dy);
+  dfree(partial);
   return rc;
 }

@@ -162,6 +162,20 @@ int gprc_gpc_get(gprc_gpc* g, int what, double* host);
 long gprc_gpc_n(const gprc_gpc* g);
 void gprc_gpc_free(gprc_gpc* g);
 
+/* ---- multi-GPU: Cholesky + solve for n beyond one GPU (BASELINE config 5) ------------------------ */
+/* One process per GPU.  K + noise I is distributed by outer panels of 512 columns (panel p on rank p mod world) and
+ * factored right-looking with panel broadcasts over NCCL (bound at run time with dlopen).  Replaces, collectively,
+ * the same reference lines as gprc_gpr_fit (R/GPRclass.R:138-153) when K does not fit one device. */
+typedef struct gprc_dist gprc_dist;
+/* rank 0 creates the 128-byte NCCL unique id; the caller ships it to the other ranks (torch.distributed, MPI, ...) */
+int gprc_dist_unique_id(char* id128, const char* nccl_path /* nullable: libnccl.so.2 */);
+int gprc_dist_create(gprc_ctx* ctx, const char* id128, int rank, int world, const char* nccl_path, gprc_dist** out);
+void gprc_dist_free(gprc_dist* d);
+/* Collective.  X (d x n), y: HOST, identical on every rank.  alpha (n, host, nullable) and logp are returned on every
+ * rank.  phase_ms (nullable, 4): build, factor, solve, total -- CUDA events on this rank's stream. */
+int gprc_dist_gpr_fit(gprc_dist* d, const gprc_kernel* k, const double* X, int dim, long n, const double* y,
+                      double noise, double* logp, double* alpha, long* info, double* phase_ms);
+
 /* ---- raw device primitives (tests, roofline microbenchmarks) ---------------------------------------------- */
 /* In-place blocked Cholesky of the lower triangle of the n x n column-major device matrix dA (ld >= n, both
  * multiples of 128).  dinv: device workspace (n/128) * 128*128 doubles receiving the inverted diagonal blocks. */
