@@ -40,13 +40,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=50000)
-    ap.add_argument("--m", type=int, default=1000000)
-    ap.add_argument("--d", type=int, default=8)
+    ap.add_argument("--train-size", dest="n", type=int, default=50000)
+    ap.add_argument("--test-size", dest="m", type=int, default=1000000)
+    ap.add_argument("--dim", dest="d", type=int, default=8)
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--cpu-sample-m", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--train", default="auto", choices=["auto", "replicated", "distributed"],
+                    help="N > 1: every rank factorises its own replica, or the factorisation itself is distributed "
+                         "(panel-cyclic, NCCL broadcasts) and assembled on every rank; auto = distributed")
     return ap.parse_args()
 
 
@@ -218,6 +221,13 @@ def main():
     import gprc_b200 as g
     ctx = g.Context(local)
     lib = ctx.lib
+    dist_train = world > 1 and args.train in ("auto", "distributed")
+    D = None
+    if dist_train:
+        from importlib import import_module
+        D = import_module("gaussian-process-regression_b200.dist").DistGPR(ctx)
+        config["sharding"] = "factorisation distributed by 512-column panels (NCCL broadcast), factor assembled on every rank; test points split across ranks"
+    dist_phase = dict(build=0.0, factor=0.0, solve=0.0)
 
     def barrier():
         ctx.sync()
@@ -251,6 +261,16 @@ def main():
     kc, _keep = spec.to_c()
 
     def step_device():
+        if dist_train:
+            # collective train (X, y are 3.6 MB: uploaded by the call), then predict on this rank's shard
+            h, lp, inf, ph = D.fit_replicated(xp, d, n, y, 0.01, spec)
+            assert inf == 0, "not positive definite: %d" % inf
+            for kk in dist_phase:
+                dist_phase[kk] += ph[kk]
+            g._lib.check(lib.gprc_gpr_predict_dev(h, dXs, m_local, dmean, dvar))
+            ctx.sync()
+            lib.gprc_gpr_free(h)
+            return lp
         h = C.c_void_p()
         logp, info = C.c_double(0.0), C.c_long(0)
         g._lib.check(lib.gprc_gpr_fit_dev(ctx.handle, kc, dX, d, n, dy, 0.01, C.byref(h), C.byref(logp), C.byref(info)))
@@ -261,6 +281,12 @@ def main():
         return logp.value
 
     def step_host():
+        if dist_train:
+            h, lp, inf, ph = D.fit_replicated(xp, d, n, y, 0.01, spec)
+            assert inf == 0
+            g._lib.check(lib.gprc_gpr_predict(h, g._lib.dptr(xsp), m_local, g._lib.dptr(mean), g._lib.dptr(var)))
+            lib.gprc_gpr_free(h)
+            return lp
         h = C.c_void_p()
         logp, info = C.c_double(0.0), C.c_long(0)
         g._lib.check(lib.gprc_gpr_fit(ctx.handle, kc, g._lib.dptr(xp), d, n, g._lib.dptr(y), 0.01, C.byref(h),
@@ -277,6 +303,8 @@ def main():
     if rank == 0:
         sampler.start()
     ctx.reset_timers()
+    for kk in dist_phase:
+        dist_phase[kk] = 0.0
     ctx.mark(0)
     t0 = time.perf_counter()
     logp = 0.0
@@ -287,6 +315,8 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ctx.elapsed_ms(0, 1)
     timers, launches = ctx.timers()
+    if dist_train:
+        timers["build_k"], timers["chol"], timers["solve"] = dist_phase["build"], dist_phase["factor"], dist_phase["solve"]
     clocks = sampler.stop() if rank == 0 else None
     sec_per_step = max_over_ranks(dev_ms / 1e3 / args.steps)
     wall_per_step = max_over_ranks(wall / args.steps)
@@ -315,7 +345,7 @@ def main():
         flops_var = float(n) * n * m_local            # algorithmic: n^2 m  
         achieved = flops_var / (var_ms * 1e-3) / 1e12 if var_ms > 0 else None
         n_pad = (n + 127) // 128 * 128
-        chol_tf = n ** 3 / 3 / (timers["chol"] / args.steps * 1e-3) / 1e12
+        chol_tf = n ** 3 / 3 / (timers["chol"] / args.steps * 1e-3) / 1e12  # aggregate over ranks when distributed
         roofline = dict(kernel="gemm_kernel<TrmmNormPolicy> (variance pass v = L^-1 K_star, fused column norms)",
                         bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
                         frac=(achieved / peak_tf) if achieved else None, traffic=None,
@@ -327,7 +357,7 @@ def main():
                     ms_per_step=sec_per_step * 1e3, higher_is_better=False, scaling="strong", vs_baseline=None,
                     dtype="f64", data="synthetic", config=config, clocks=clocks, e2e=e2e,
                     gpu_launches=int(launches), roofline=roofline,
-                    cholesky_tflops=chol_tf, cholesky_frac_of_peak=chol_tf / peak_tf,
+                    cholesky_tflops=chol_tf, cholesky_frac_of_peak=chol_tf / (peak_tf * (world if dist_train else 1)),
                     test_pts_per_s=m / sec_per_step, wall_s_per_step=wall_per_step, logp=logp,
                     phase_ms_per_step={k: v / args.steps for k, v in timers.items() if v})
         if not args.no_cpu_baseline and world == 1:
@@ -335,6 +365,8 @@ def main():
             line["cpu_baseline"] = dict(value=ref["value"], unit="s", cores=ref["cores"], kind=ref["kind"],
                                         sample=ref["sample"])
         print(json.dumps(line))
+    if D is not None:
+        D.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

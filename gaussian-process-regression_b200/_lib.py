@@ -89,6 +89,8 @@ SIGNATURES = {
     "gprc_dist_free": (None, [_P]),
     "gprc_dist_gpr_fit": (C.c_int, [_P, _K, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double, c_double_p,
                                     c_double_p, c_long_p, c_double_p]),
+    "gprc_dist_gpr_fit_replicated": (C.c_int, [_P, _K, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double,
+                                               C.POINTER(_P), c_double_p, c_long_p, c_double_p]),
     "gprc_dev_potrf": (C.c_int, [_P, _P, C.c_long, C.c_long, _P, c_long_p]),
     "gprc_dev_dgemm": (C.c_int, [_P, C.c_int, C.c_long, C.c_long, C.c_long, C.c_double, _P, C.c_long, _P, C.c_long,
                                  C.c_double, _P, C.c_long]),

@@ -1514,9 +1514,13 @@ extern "C" void gprc_dist_free(gprc_dist* D) {
   delete D;
 }
 
-extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n, const double* y,
-                                 double noise, double* logp, double* alpha, long* info, double* phase_ms) {
+// replicate != nullptr: every rank also assembles the complete factor from the panels it receives anyway (no extra
+// communication) and gets an ordinary gprc_gpr handle back, ready for gprc_gpr_predict on its shard of test points.
+static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                         double noise, double* logp, double* alpha, long* info, double* phase_ms,
+                         gprc_gpr** replicate) {
   GPRC_ARG(D && k && X && y && logp && info && n > 0 && d > 0 && noise >= 0.0);
+  if (replicate) *replicate = nullptr;
   gprc_ctx* c = D->ctx;
   DeviceGuard guard(c);
   NcclApi& api = D->api;
@@ -1531,8 +1535,18 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
     GPRC_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM_BYTES));
     configured[c->device & 63] = true;
   }
-  SpecHolder spec;
+  gprc_gpr* g = nullptr;
+  SpecHolder local_spec;
+  if (replicate) {
+    g = new gprc_gpr();
+    g->ctx = c;
+    g->d = d;
+    g->noise = noise;
+    g->khost = *k;
+  }
+  SpecHolder& spec = g ? g->spec : local_spec;
   GPRC_CHECK(make_spec(c, k, d, spec));
+  const long pbuf_elems = slab + (long)OUTER_BLOCKS * NB * NB;  // panel + its 4 inverted diagonal blocks
   double *dX = nullptr, *Aloc = nullptr, *dinv = nullptr, *diag = nullptr, *Pbuf[2] = {nullptr, nullptr}, *vec = nullptr,
          *dy = nullptr, *partial = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
@@ -1541,10 +1555,15 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
   do {
     if ((rc = dmalloc(&dX, (size_t)d * n)) || (rc = dmalloc(&Aloc, (size_t)std::max(nown, 1) * slab)) ||
         (rc = dmalloc(&dinv, (size_t)n_pad * NB)) || (rc = dmalloc(&diag, (size_t)n_pad)) ||
-        (rc = dmalloc(&Pbuf[0], (size_t)slab)) || (rc = dmalloc(&Pbuf[1], (size_t)slab)) ||
+        (rc = dmalloc(&Pbuf[0], (size_t)pbuf_elems)) || (rc = dmalloc(&Pbuf[1], (size_t)pbuf_elems)) ||
         (rc = dmalloc(&vec, (size_t)2 * n_pad)) || (rc = dmalloc(&dy, (size_t)n_pad)) ||
         (rc = dmalloc(&partial, (size_t)((n_pad + BWD_CHUNK - 1) / BWD_CHUNK) * NB)))
       break;
+    if (g) {
+      g->F.n = n;
+      g->F.n_pad = n_pad;
+      if ((rc = dmalloc(&g->F.L, (size_t)n_pad * n_pad)) || (rc = dmalloc(&g->alpha, (size_t)n_pad))) break;
+    }
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventCreate(&e2);
@@ -1607,7 +1626,21 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
       const long rows = n_pad - (long)p * PANEL;
       GPRC_CUDA(cudaMemcpy2DAsync(Pbuf[p & 1], rows * sizeof(double), Av + (long)p * PANEL * n_pad + (long)p * PANEL,
                                   n_pad * sizeof(double), rows * sizeof(double), PANEL, cudaMemcpyDeviceToDevice, s1));
+      GPRC_CUDA(cudaMemcpyAsync(Pbuf[p & 1] + rows * PANEL, dinv + (long)J0 * NB * NB,
+                                sizeof(double) * OUTER_BLOCKS * NB * NB, cudaMemcpyDeviceToDevice, s1));
       GPRC_CUDA(cudaEventRecord(D->ev_packed, s1));
+      return 0;
+    };
+    // assemble the complete factor from the broadcast panels (replicated handle only)
+    auto unpack = [&](int p) -> int {
+      if (!g) return 0;
+      const long rows = n_pad - (long)p * PANEL;
+      GPRC_CUDA(cudaMemcpy2DAsync(g->F.L + (long)p * PANEL * n_pad + (long)p * PANEL, n_pad * sizeof(double),
+                                  Pbuf[p & 1], rows * sizeof(double), rows * sizeof(double), PANEL,
+                                  cudaMemcpyDeviceToDevice, s0));
+      if (p % N != me)
+        GPRC_CUDA(cudaMemcpyAsync(dinv + (long)p * OUTER_BLOCKS * NB * NB, Pbuf[p & 1] + rows * PANEL,
+                                  sizeof(double) * OUTER_BLOCKS * NB * NB, cudaMemcpyDeviceToDevice, s0));
       return 0;
     };
     auto update = [&](int p, int first_panel, int count, cudaStream_t st) -> int {
@@ -1641,7 +1674,8 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
       if ((rc = factor_panel(0))) break;
       GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
     }
-    GPRC_NCCL(api, api.Broadcast(Pbuf[0], Pbuf[0], (size_t)n_pad * PANEL, ncclDouble, owner(0), D->comm, sc));
+    GPRC_NCCL(api, api.Broadcast(Pbuf[0], Pbuf[0], (size_t)n_pad * PANEL + OUTER_BLOCKS * NB * NB, ncclDouble, owner(0),
+                                 D->comm, sc));
     GPRC_CUDA(cudaEventRecord(D->ev_bcast[0], sc));
     for (int p = 0; p < npan && rc == 0; ++p) {
       const bool own_next = (p + 1 < npan) && owner(p + 1) == me;
@@ -1657,12 +1691,14 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
         if (p > 0) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_rest, 0));
         if (own_next) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
         const long rows = n_pad - (long)(p + 1) * PANEL;
-        GPRC_NCCL(api, api.Broadcast(Pbuf[(p + 1) & 1], Pbuf[(p + 1) & 1], (size_t)rows * PANEL, ncclDouble,
-                                     owner(p + 1), D->comm, sc));
+        GPRC_NCCL(api, api.Broadcast(Pbuf[(p + 1) & 1], Pbuf[(p + 1) & 1],
+                                     (size_t)rows * PANEL + OUTER_BLOCKS * NB * NB, ncclDouble, owner(p + 1), D->comm,
+                                     sc));
         GPRC_CUDA(cudaEventRecord(D->ev_bcast[(p + 1) & 1], sc));
       }
       // rest(p): every owned panel right of p (and right of p + 1 if that one was just handled by LA)
       GPRC_CUDA(cudaStreamWaitEvent(s0, D->ev_bcast[p & 1], 0));
+      if ((rc = unpack(p))) break;
       const int first = next_owned_after(own_next ? p + 1 : p);
       const int count = (first < npan) ? (npan - 1 - first) / N + 1 : 0;
       if ((rc = update(p, first, count, s0))) break;
@@ -1676,9 +1712,14 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
     GPRC_NCCL(api, api.AllReduce(c->d_info, c->d_info, 1, ncclInt64, ncclMin, D->comm, s0));
     cudaEventRecord(e2, s0);
 
-    // ---- alpha = L^-T L^-1 y: panels in order, the right-hand side travels by broadcast ----
     double* bw = vec;           // working right-hand side
     double* xs = vec + n_pad;   // solution of the current sweep
+    if (g) {
+      // the factor is complete on every rank: ordinary single-GPU solves
+      if ((rc = potrs_vec(c, g->F.L, n_pad, n_pad, dinv, dy, bw, xs, g->alpha))) break;
+      cudaMemcpyAsync(xs, g->alpha, sizeof(double) * n_pad, cudaMemcpyDeviceToDevice, s0);
+    } else {
+    // ---- alpha = L^-T L^-1 y: panels in order, the right-hand side travels by broadcast ----
     cudaMemcpyAsync(bw, dy, sizeof(double) * n_pad, cudaMemcpyDeviceToDevice, s0);
     cudaMemsetAsync(xs, 0, sizeof(double) * n_pad, s0);
     for (int p = 0; p < npan; ++p) {
@@ -1711,6 +1752,7 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
       }
       GPRC_NCCL(api, api.Broadcast(xs, xs, (size_t)n_pad, ncclDouble, owner(p), D->comm, s0));
     }
+    }
     gp_reduce_kernel<<<1, 1024, 0, s0>>>(dy, xs, diag, n, c->d_scalars);
     c->launches++;
     cudaEventRecord(e3, s0);
@@ -1741,6 +1783,19 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
   cudaStreamSynchronize(s0);
   for (cudaEvent_t ev : {e0, e1, e2, e3})
     if (ev) cudaEventDestroy(ev);
+  if (g) {
+    if (rc == 0 && *info == 0) {
+      g->X = dX;
+      g->y = dy;
+      g->F.dinv = dinv;
+      g->F.diag = diag;
+      g->logp = *logp;
+      dX = dy = dinv = diag = nullptr;
+      *replicate = g;
+    } else {
+      gpr_destroy(g);
+    }
+  }
   dfree(dX);
   dfree(Aloc);
   dfree(dinv);
@@ -1751,4 +1806,16 @@ extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const doubl
   dfree(dy);
   dfree(partial);
   return rc;
+}
+
+extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                                 double noise, double* logp, double* alpha, long* info, double* phase_ms) {
+  return dist_fit_impl(D, k, X, d, n, y, noise, logp, alpha, info, phase_ms, nullptr);
+}
+
+extern "C" int gprc_dist_gpr_fit_replicated(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n,
+                                            const double* y, double noise, gprc_gpr** out, double* logp, long* info,
+                                            double* phase_ms) {
+  GPRC_ARG(out != nullptr);
+  return dist_fit_impl(D, k, X, d, n, y, noise, logp, nullptr, info, phase_ms, out);
 }

@@ -63,3 +63,15 @@ class DistGPR:
                                                   C.byref(info), phases))
         return dict(logp=logp.value, alpha=alpha, info=info.value,
                     phase_ms=dict(build=phases[0], factor=phases[1], solve=phases[2], total=phases[3]))
+
+    def fit_replicated(self, xp, d, n, y, noise, spec: KernelSpec):
+        """Collective train; every rank gets an ordinary model handle (gprc_gpr*) holding the complete factor.
+        xp: the ABI's point-major buffer (n x d C-contiguous).  -> (handle, logp, info, phase_ms)"""
+        kc, keep = spec.to_c()
+        h = _lib._P()
+        logp, info = C.c_double(0.0), C.c_long(0)
+        phases = (C.c_double * 4)()
+        _lib.check(self.ctx.lib.gprc_dist_gpr_fit_replicated(self.handle, kc, _lib.dptr(xp), d, n, _lib.dptr(y),
+                                                             float(noise), C.byref(h), C.byref(logp), C.byref(info),
+                                                             phases))
+        return h, logp.value, info.value, dict(build=phases[0], factor=phases[1], solve=phases[2], total=phases[3])

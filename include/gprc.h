@@ -176,6 +176,11 @@ void gprc_dist_free(gprc_dist* d);
 int gprc_dist_gpr_fit(gprc_dist* d, const gprc_kernel* k, const double* X, int dim, long n, const double* y,
                       double noise, double* logp, double* alpha, long* info, double* phase_ms);
 
+/* Same collective factorisation, but every rank also assembles the complete factor from the panels it receives anyway
+ * and gets an ordinary model handle: train on N GPUs, then gprc_gpr_predict on each rank's shard of test points. */
+int gprc_dist_gpr_fit_replicated(gprc_dist* d, const gprc_kernel* k, const double* X, int dim, long n, const double* y,
+                                 double noise, gprc_gpr** out, double* logp, long* info, double* phase_ms);
+
 /* ---- raw device primitives (tests, roofline microbenchmarks) ---------------------------------------------- */
 /* In-place blocked Cholesky of the lower triangle of the n x n column-major device matrix dA (ld >= n, both
  * multiples of 128).  dinv: device workspace (n/128) * 128*128 doubles receiving the inverted diagonal blocks. */
