@@ -346,7 +346,10 @@ def main():
         achieved = flops_var / (var_ms * 1e-3) / 1e12 if var_ms > 0 else None
         n_pad = (n + 127) // 128 * 128
         chol_tf = n ** 3 / 3 / (timers["chol"] / args.steps * 1e-3) / 1e12  # aggregate over ranks when distributed
-        roofline = dict(kernel="gemm_kernel<TrmmNormPolicy> (variance pass v = L^-1 K_star, fused column norms)",
+        kname = ("gemm_kernel<TrsmLeftUpdatePolicy> (variance pass v = L^-1 K_star by blocked substitution, K_star^T "
+                 "updated in place; column norms fused into gemm_kernel<TrsmLeftDiagPolicy>)") if not timers["trtri"] \
+            else "gemm_kernel<TrmmNormPolicy> (variance pass v = (L^-1) K_star, fused column norms)"
+        roofline = dict(kernel=kname,
                         bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
                         frac=(achieved / peak_tf) if achieved else None, traffic=None,
                         peak_source="cuBLAS Dgemm fp64 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json "

@@ -21,6 +21,7 @@ KERNEL_IDS = dict(constant=CONSTANT, linear=LINEAR, polynomial=POLYNOMIAL, sqrex
 GET_L, GET_ALPHA, GET_LINV, GET_FHAT, GET_SQRTW = range(5)
 GRAD_AS_CODED, GRAD_TEXTBOOK = 0, 1
 OPT_GRAM_DMMA = 1
+OPT_PREDICT_PATH = 2
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "spare"]
 
 

@@ -67,6 +67,7 @@ struct gprc_ctx {
   cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr;
   int sm_count = 148;
   int opt_gram_dmma = 1;
+  int opt_predict_path = 0;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};
   // pending (start, stop, phase) events; resolved lazily in gprc_ctx_get_timers so that timing never adds a sync

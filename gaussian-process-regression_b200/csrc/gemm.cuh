@@ -436,6 +436,115 @@ struct TrmmNormPolicy {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Predictive variance without forming L^-1: blocked forward substitution on the transposed right-hand side
+// T = K_star^T (mc x n, test point contiguous).  For block row i = 0, 1, ...:
+//   TrsmLeftUpdatePolicy   T[:, i] -= V[:, <i] L[i, <i]^T      i.e.  R_i = Ks_i - L[i, <i] V[<i]      (K = 128 i)
+//   TrsmLeftDiagPolicy     V_i = Linv_i R_i  in place, and partial[i][t] = sum over the block's rows of V^2
+// One CTA per tile of 128 test points: with chunks of 148 * 128 test points every launch is exactly one wave.
+// Costs n^2 m flops like the W-based pass but skips the n^3/3 inversion (the Amdahl term when a factor is shared by
+// many GPUs that each predict a shard).
+// ---------------------------------------------------------------------------------------------------------------
+struct TrsmLeftUpdatePolicy {
+  static constexpr bool B_KMAJOR = false;
+  const double* L;
+  long ldl;
+  double* T;
+  long ldt;
+  int i;
+  struct Tile {
+    double* C;  // element (m, n) of the tile at C[n + m * ldt]
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    const int tc = blockIdx.x;
+    w.A = L + (long)i * NB;
+    w.lda = ldl;
+    w.B = T + (long)tc * NB;  // element (k, n) = V[k, t] = T[t + k * ldt]
+    w.ldb = ldt;
+    w.k_begin = 0;
+    w.k_end = i * NB;
+    t.C = T + (long)tc * NB + (long)i * NB * ldt;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile& t) const {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int line = threadIdx.x + q * GEMM_CONSUMERS;
+      prefetch_l2(t.C + (long)(line >> 3) * ldt + (line & 7) * 16);
+    }
+  }
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double*) const {
+    const WarpCoord wc;
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+      double* cp = t.C + (long)wc.row(mb) * ldt;
+      double2 v[4];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) v[nb] = *reinterpret_cast<const double2*>(cp + wc.col(nb, 0));
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        v[nb].x -= acc[mb][nb][0];
+        v[nb].y -= acc[mb][nb][1];
+        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = v[nb];
+      }
+    }
+  }
+};
+
+struct TrsmLeftDiagPolicy {
+  static constexpr bool B_KMAJOR = false;
+  const double* linv;  // inverted diagonal block i: element (m, k) at linv[m + k * 128]
+  double* T;
+  long ldt;
+  int i;
+  double* partial;  // [n_tiles][ldp]
+  long ldp;
+  struct Tile {
+    double* C;
+    int tc;
+  };
+  __device__ __forceinline__ bool setup(TileWork& w, Tile& t) const {
+    t.tc = blockIdx.x;
+    t.C = T + (long)t.tc * NB + (long)i * NB * ldt;
+    w.A = linv;
+    w.lda = NB;
+    w.B = t.C;  // element (k, n) = R_i[k, t]
+    w.ldb = ldt;
+    w.k_begin = 0;
+    w.k_end = NB;
+    return true;
+  }
+  __device__ __forceinline__ void prefetch(const Tile&) const {}
+  __device__ __forceinline__ void epilogue(const Tile& t, Acc& acc, double* smem) const {
+    const WarpCoord wc;
+    // all 8 k-slices of the tile have been consumed: overwrite R_i by V_i (in place, transposed storage)
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+      double* cp = t.C + (long)wc.row(mb) * ldt;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        *reinterpret_cast<double2*>(cp + wc.col(nb, 0)) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+    }
+    consumer_sync();
+    double* red = smem;  // [2][128]
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb) s = fma(acc[mb][nb][r], acc[mb][nb][r], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if ((wc.lane >> 2) == 0) red[wc.warp_m * 128 + wc.col(nb, r)] = s;
+      }
+    consumer_sync();
+    if (threadIdx.x < 128)
+      partial[(long)i * ldp + (long)t.tc * NB + threadIdx.x] = red[threadIdx.x] + red[128 + threadIdx.x];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // Plain DGEMM (tests, roofline microbenchmark):  C = beta C + alpha A op(B)
 // ---------------------------------------------------------------------------------------------------------------
 template <bool KMAJOR>

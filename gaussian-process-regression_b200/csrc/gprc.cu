@@ -335,6 +335,11 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     c->opt_gram_dmma = value;
     return 0;
   }
+  if (option == GPRC_OPT_PREDICT_PATH) {
+    GPRC_ARG(value >= 0 && value <= 2);
+    c->opt_predict_path = value;
+    return 0;
+  }
   return set_error(-1, __FILE__, __LINE__, "unknown option");
 }
 
@@ -573,6 +578,8 @@ static int ensure_inverse(gprc_ctx* c, FactorState& F) {
   return rc;
 }
 
+constexpr long WAVE_COLS = 148L * NB;  // test points of one full wave of 128-wide tiles on 148 SMs
+
 static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -583,6 +590,7 @@ static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long 
   long cap = (long)(budget / per_col) / NB * NB;
   cap = std::max<long>(cap, NB);
   cap = std::min<long>(cap, 1L << 20);
+  if (cap >= WAVE_COLS) cap = cap / WAVE_COLS * WAVE_COLS;  // chunks made of whole waves
   want = std::min(want, cap);
   if (ws.mc >= want) return 0;
   ws.release();
@@ -613,11 +621,28 @@ static int variance_pass(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long
   return launch_gemm(c, p, dim3((unsigned)(groups * TrmmNormPolicy::GROUP * ntc)));
 }
 
+// the same partial column norms by blocked forward substitution on K_star^T (no inverse needed)
+static int variance_pass_trsm(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur_pad) {
+  const int nt = (int)(F.n_pad / NB), ntc = (int)(mcur_pad / NB);
+  PhaseTimer t(c, GPRC_T_VAR);
+  for (int i = 0; i < nt; ++i) {
+    if (i > 0) {
+      TrsmLeftUpdatePolicy up{F.L, F.n_pad, ws.Ks, ws.mc, i};
+      GPRC_CHECK(launch_gemm(c, up, dim3((unsigned)ntc)));
+    }
+    TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};
+    GPRC_CHECK(launch_gemm(c, dg, dim3((unsigned)ntc)));
+  }
+  return 0;
+}
+
 // mean/var for m test points (device pointers).  weights: alpha (GPR) or (y+1)/2 - P (GPC); rowscale: sqrt(W) or null.
 static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F,
                                  PredictWorkspace& ws, const double* weights, const double* rowscale,
                                  const double* dXs, long m, double* dmean, double* dvar) {
-  GPRC_CHECK(ensure_inverse(c, F));
+  // path of the variance pass: with W = L^-1 (one launch per chunk) or by blocked substitution (no inversion)
+  const bool use_trsm = (c->opt_predict_path == 2) || (c->opt_predict_path == 0 && !F.W && m >= WAVE_COLS);
+  if (!use_trsm) GPRC_CHECK(ensure_inverse(c, F));
   GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
   for (long c0 = 0; c0 < m; c0 += ws.mc) {
     const long mcur = std::min(ws.mc, m - c0);
@@ -632,7 +657,10 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
                                                                                  mcur, ws.kss);
       c->launches++;
     }
-    GPRC_CHECK(variance_pass(c, F, ws, mpad, nullptr, 0));
+    if (use_trsm)
+      GPRC_CHECK(variance_pass_trsm(c, F, ws, mpad));
+    else
+      GPRC_CHECK(variance_pass(c, F, ws, mpad, nullptr, 0));
     finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
         ws.pmean, ws.mc, (int)(F.n_pad / CT), ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, dmean + c0,
         dvar + c0);

@@ -48,8 +48,11 @@ typedef struct {
 
 /* flags for gprc_ctx_set_option */
 enum {
-  GPRC_OPT_GRAM_DMMA = 1 /* 1 (default): dot-product / norm-expansion builds use the FP64 tensor-core Gram tile
-                            kernel when d >= 4; 0: always direct differences as R/GPRclass.R:394 writes them */
+  GPRC_OPT_GRAM_DMMA = 1, /* reserved: FP64 tensor-core Gram-tile build (not implemented; builds use direct
+                             differences exactly as R/GPRclass.R:394 writes them) */
+  GPRC_OPT_PREDICT_PATH = 2 /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
+                               (one launch per chunk; best for repeated / small predicts), 2 blocked substitution
+                               (no n^3/3 inversion; chosen automatically for >= 18 944 test points) */
 };
 
 /* what to fetch with gprc_gpr_get / gprc_gpc_get */

@@ -164,3 +164,37 @@ def test_large_size_properties(gprc):
     # predicting at training points reproduces y up to the noise shrinkage: mean = y - noise * alpha
     ptrain = g.predict(X[:, :256])
     np.testing.assert_allclose(ptrain[:, 0], y[:256] - 0.01 * g.alpha[:256], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
+    """v = L^-1 K_star either with the explicit inverse (one triangular GEMM) or by blocked substitution."""
+    rng = np.random.default_rng(31)
+    n, m, D = 700, 450, 5
+    X = rng.uniform(-1, 1, (D, n))
+    y = np.sum(np.cos(X), axis=0) + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-1, 1, (D, m))
+    ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
+    try:
+        got = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.rationalquadratic, l=0.8, alpha=1.5), ctx=ctx).predict(Xs)
+    finally:
+        ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
+    ok = oracle.cov_func(oracle.rationalquadratic, l=0.8, alpha=1.5)
+    ref = oracle.GPR(X, y, 0.05, ok).predict(Xs)
+    assert_mean_var(got, ref, ok(Xs, Xs))
+
+
+def test_large_predict_takes_the_substitution_path(gprc, oracle, ctx):
+    # >= 148 * 128 test points and no inverse yet: automatic choice = blocked substitution, whole-wave chunks
+    rng = np.random.default_rng(32)
+    n, m = 300, 148 * 128 + 77
+    X = rng.uniform(-6, 6, (1, n))
+    y = 0.1 * X[0] ** 3 + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-6, 6, (1, m))
+    g = gprc.GPR(X, y, 0.01, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    ctx.reset_timers()
+    got = g.predict(Xs)
+    timers, launches = ctx.timers()
+    assert timers["trtri"] == 0.0 and timers["var"] > 0.0
+    ref = oracle.GPR(X, y, 0.01, oracle.cov_func(oracle.sqrexp, l=1.0)).predict(Xs)
+    assert_mean_var(got, ref, np.ones(m))
