@@ -198,3 +198,32 @@ def test_large_predict_takes_the_substitution_path(gprc, oracle, ctx):
     assert timers["trtri"] == 0.0 and timers["var"] > 0.0
     ref = oracle.GPR(X, y, 0.01, oracle.cov_func(oracle.sqrexp, l=1.0)).predict(Xs)
     assert_mean_var(got, ref, np.ones(m))
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 3), (127, 5), (128, 128), (129, 1), (513, 257)])
+def test_edge_sizes(gprc, oracle, n, m):
+    # padding boundaries of the 128-blocked kernels and degenerate sizes
+    rng = np.random.default_rng(n * 7 + m)
+    X = rng.uniform(-2, 2, (3, n))
+    y = rng.standard_normal(n)
+    Xs = rng.uniform(-2, 2, (3, m))
+    g = gprc.GPR(X, y, 0.3, gprc.cov_func(gprc.gammaexp, l=1.2, gamma=1.3))
+    ok = oracle.cov_func(oracle.gammaexp, l=1.2, gamma=1.3)
+    o = oracle.GPR(X, y, 0.3, ok)
+    assert abs(g.logp[0, 0] - o.logp) <= LOGP_RTOL * abs(o.logp)
+    assert_mean_var(g.predict(Xs), o.predict(Xs), ok(Xs, Xs))
+    assert g.L.shape == (n, n) and g.alpha.shape == (n,)
+
+
+def test_linear_kernel_with_per_dimension_sigma(gprc, oracle):
+    rng = np.random.default_rng(41)
+    X = rng.standard_normal((3, 90))
+    y = X[0] - 2 * X[2] + rng.normal(0, 0.1, 90)
+    sig = np.array([0.5, 2.0, 1.25])
+    g = gprc.GPR.linear.new(X, y, 0.2, sig)
+    o = oracle.GPR(X, y, 0.2, oracle.cov_func(oracle.linear, sigma=sig))
+    Xs = rng.standard_normal((3, 40))
+    ok = oracle.cov_func(oracle.linear, sigma=sig)
+    assert_mean_var(g.predict(Xs), o.predict(Xs), np.abs(ok(Xs, Xs)))
+    with pytest.raises(ValueError):
+        gprc.GPR.linear.new(X, y, 0.2, np.array([1.0, 2.0]))  # stopifnot(length(sigma) == nrow(X))
