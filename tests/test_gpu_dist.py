@@ -1,0 +1,46 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box, otherwise skipped): distributed Cholesky + solve and the
+train-distributed / predict-sharded flow against the single-GPU path, launched the way the driver launches bench.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _torchrun(script, *args, nproc=2, port=29541):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), script] + list(args)
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+
+
+def test_distributed_cholesky_matches_single_gpu():
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun("tools/dist_check.py", "1000", "3000", "8192")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 3
+    for d in lines:
+        assert d["info"] == 0
+        assert d["logp_rel_diff"] <= 1e-12      # north_star: 1e-8 on the log marginal likelihood
+        assert d["alpha_max_rel_diff"] <= 1e-10
+
+
+def test_distributed_train_then_sharded_predict_is_bitwise_the_single_gpu_result():
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun("tools/dist_predict_check.py", port=29542)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [l for l in r.stdout.splitlines() if l.startswith("rank")]
+    assert len(rows) == 6
+    for l in rows:
+        assert "max|dmean| 0.00e+00" in l and "max|dvar| 0.00e+00" in l and "info 0" in l
