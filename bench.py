@@ -68,11 +68,14 @@ def make_inputs(n, m, d):
 def cpu_reference(n, m, d, ns, ms, steps=1, warmup=0):
     import scipy.linalg
     from oracle import gprc_oracle as o
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its workers: undo that here)
+    threads = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=threads)
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        threads = os.cpu_count() or 1
+        pass
     X, y, Xs = make_inputs(ns, ms, d)
     k = o.cov_func(o.sqrexp, l=1.0)
     times = []

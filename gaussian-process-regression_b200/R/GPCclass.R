@@ -32,6 +32,9 @@ GPC <- R6::R6Class("GPC",
       if (!is.matrix(X_star)) dim(X_star) <- c(1, length(X_star))
       storage.mode(X_star) <- "double"
       spec <- .gprc_spec(private$.k)
+      # built-in kernels: latent prediction and the integrate() loop in one device call (dqagi port, same tolerances)
+      if (!is.null(spec) && !isFALSE(getOption("gprc.device_quadrature")))
+        return(.Call(C_gprc_gpc_predict_class, private$.ptr, X_star))
       lat <- if (!is.null(spec)) .Call(C_gprc_gpc_predict_latent, private$.ptr, X_star, NULL, NULL)
              else .Call(C_gprc_gpc_predict_latent, private$.ptr, NULL, covariance_matrix(private$.X, X_star, private$.k),
                         as.double(private$.k(X_star, X_star)))

@@ -82,6 +82,8 @@ SIGNATURES = {
                                            c_int_p]),
     "gprc_gpc_predict_latent": (C.c_int, [_P, c_double_p, C.c_long, c_double_p, c_double_p]),
     "gprc_gpc_predict_latent_precomputed": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, c_double_p]),
+    "gprc_gpc_predict_class": (C.c_int, [_P, c_double_p, C.c_long, c_double_p, c_int_p]),
+    "gprc_logistic_gaussian": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, c_int_p]),
     "gprc_gpc_get": (C.c_int, [_P, C.c_int, c_double_p]),
     "gprc_gpc_n": (C.c_long, [_P]),
     "gprc_gpc_free": (None, [_P]),

@@ -9,6 +9,7 @@
 #include "potrf.cuh"
 #include "trsv.cuh"
 #include "gpc.cuh"
+#include "quad.cuh"
 
 namespace gprc {
 thread_local std::string g_last_error;
@@ -1410,6 +1411,87 @@ extern "C" int gprc_gpc_predict_latent_precomputed(gprc_gpc* g, const double* Ks
   DeviceGuard guard(g->ctx);
   return predict_precomputed(g->ctx, g->F, g->ws, g->gradl, g->sw, Ks, kss, m, fs_bar, Vfs);
 }
+// one thread per test point: the adaptive QUADPACK recursion runs in the thread's local memory
+__global__ void __launch_bounds__(128) logistic_gaussian_kernel(const double* __restrict__ mean,
+                                                                const double* __restrict__ sd, long m,
+                                                                double* __restrict__ out, int* __restrict__ ier) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double mu = mean[i], s = sd[i];
+  if (!(s > 0.0) || !isfinite(mu) || !isfinite(s)) {  // dnorm(sd <= 0) is NaN: integrate() stops with "non-finite function value"
+    out[i] = NAN;
+    if (ier) ier[i] = -1;
+    return;
+  }
+  const gprc_quad::QuadResult r = gprc_quad::logistic_gaussian(mu, s);
+  out[i] = r.result;
+  if (ier) ier[i] = r.ier;
+}
+
+static int quad_dev(gprc_ctx* c, const double* dmean, const double* dsd, long m, double* dout, int* dier) {
+  logistic_gaussian_kernel<<<(unsigned)((m + 127) / 128), 128, 0, c->stream>>>(dmean, dsd, m, dout, dier);
+  c->launches++;
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gprc_logistic_gaussian(gprc_ctx* c, const double* mean, const double* sd, long m, double* out, int* ier) {
+  GPRC_ARG(c && mean && sd && out && m >= 0);
+  if (m == 0) return 0;
+  DeviceGuard guard(c);
+  double *dm = nullptr, *ds = nullptr, *dout = nullptr;
+  int* dier = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dm, (size_t)m)) || (rc = dmalloc(&ds, (size_t)m)) || (rc = dmalloc(&dout, (size_t)m)) ||
+        (rc = dmalloc(&dier, (size_t)m)))
+      break;
+    cudaMemcpyAsync(dm, mean, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(ds, sd, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream);
+    if ((rc = quad_dev(c, dm, ds, m, dout, dier))) break;
+    cudaMemcpyAsync(out, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    if (ier) cudaMemcpyAsync(ier, dier, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dm);
+  dfree(ds);
+  dfree(dout);
+  dfree(dier);
+  return rc;
+}
+
+extern "C" int gprc_gpc_predict_class(gprc_gpc* g, const double* Xs, long m, double* prob, int* ier) {
+  GPRC_ARG(g && Xs && prob && m >= 0);
+  GPRC_ARG(!g->precomputed);
+  if (m == 0) return 0;
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c);
+  double *dXs = nullptr, *dmean = nullptr, *dvar = nullptr, *dout = nullptr;
+  int* dier = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dXs, (size_t)g->d * m)) || (rc = dmalloc(&dmean, (size_t)m)) || (rc = dmalloc(&dvar, (size_t)m)) ||
+        (rc = dmalloc(&dout, (size_t)m)) || (rc = dmalloc(&dier, (size_t)m)))
+      break;
+    cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar)))
+      break;
+    // dnorm(z, mean = fs_bar[i], sd = Vfs[i]): the latent VARIANCE is passed as sd, as the reference does (A.1)
+    if ((rc = quad_dev(c, dmean, dvar, m, dout, dier))) break;
+    cudaMemcpyAsync(prob, dout, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    if (ier) cudaMemcpyAsync(ier, dier, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  dfree(dXs);
+  dfree(dmean);
+  dfree(dvar);
+  dfree(dout);
+  dfree(dier);
+  return rc;
+}
+
 extern "C" int gprc_gpc_get(gprc_gpc* g, int what, double* host) {
   GPRC_ARG(g && host);
   gprc_ctx* c = g->ctx;

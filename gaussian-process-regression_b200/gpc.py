@@ -131,7 +131,38 @@ class GPC:
                                                                _lib.dptr(fs_bar), _lib.dptr(Vfs)))
         return fs_bar, Vfs
 
-    def predict_class(self, X_star):
-        """R/GPCclass.R:108-118; the integral passes the latent variance as ``sd`` like the reference (A.1)."""
-        fs_bar, Vfs = self.predict_latent(X_star)
-        return np.array([logistic_gaussian_integral(m, s) for m, s in zip(fs_bar, Vfs)])
+    _IER_MESSAGES = {1: "maximum number of subdivisions reached", 2: "roundoff error was detected",
+                     3: "extremely bad integrand behaviour", 4: "roundoff error is detected in the extrapolation table",
+                     5: "the integral is probably divergent", 6: "the input is invalid",
+                     -1: "non-finite function value"}
+
+    def predict_class(self, X_star, quadrature="device"):
+        """R/GPCclass.R:108-118; the integral passes the latent variance as ``sd`` like the reference (A.1).
+
+        quadrature="device": latent prediction and the QUADPACK dqagi port in one library call
+        (gprc_gpc_predict_class); "host": scipy's QUADPACK per point, as the reference loops over integrate()."""
+        X_star = np.asarray(X_star, dtype=np.float64)
+        if X_star.ndim < 2:
+            X_star = X_star.reshape(1, -1)
+        if quadrature == "host":
+            fs_bar, Vfs = self.predict_latent(X_star)
+            return np.array([logistic_gaussian_integral(m, s) for m, s in zip(fs_bar, Vfs)])
+        m = X_star.shape[1]
+        prob = np.empty(m)
+        ier = np.zeros(m, dtype=np.int32)
+        lib = self._ctx.lib
+        if kernel_spec_of(self._k) is not None:
+            if X_star.shape[0] != self._X.shape[0]:
+                raise ValueError("non-conformable arguments")
+            xs = _lib.points(X_star)
+            _lib.check(lib.gprc_gpc_predict_class(self._handle, _lib.dptr(xs), m, _lib.dptr(prob),
+                                                  ier.ctypes.data_as(_lib.c_int_p)))
+        else:
+            fs_bar, Vfs = self.predict_latent(X_star)
+            _lib.check(lib.gprc_logistic_gaussian(self._ctx.handle, _lib.dptr(np.ascontiguousarray(fs_bar)),
+                                                  _lib.dptr(np.ascontiguousarray(Vfs)), m, _lib.dptr(prob),
+                                                  ier.ctypes.data_as(_lib.c_int_p)))
+        bad = np.flatnonzero(ier != 0)
+        if bad.size:  # integrate(stop.on.error = TRUE)
+            raise FloatingPointError(self._IER_MESSAGES.get(int(ier[bad[0]]), "integrate() failed"))
+        return prob

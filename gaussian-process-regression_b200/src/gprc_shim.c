@@ -193,6 +193,28 @@ SEXP C_gprc_gpc_predict_latent(SEXP ptr, SEXP Xs, SEXP Ks, SEXP kss) {
   return out;
 }
 
+/* $predict_class complete on the device (latent prediction + QUADPACK dqagi per point), R/GPCclass.R:108-118.
+ * Returns the probabilities; a non-zero QUADPACK code raises the message integrate() would raise. */
+SEXP C_gprc_gpc_predict_class(SEXP ptr, SEXP Xs) {
+  static const char* msg[] = {"", "maximum number of subdivisions reached", "roundoff error was detected",
+                              "extremely bad integrand behaviour",
+                              "roundoff error is detected in the extrapolation table",
+                              "the integral is probably divergent", "the input is invalid"};
+  gprc_gpc* g = (gprc_gpc*)R_ExternalPtrAddr(ptr);
+  if (!g) Rf_error("gprc: model handle is NULL");
+  const long m = Rf_ncols(Xs);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, m));
+  int* ier = (int*)R_alloc((size_t)m, sizeof(int));
+  int rc = gprc_gpc_predict_class(g, REAL(Xs), m, REAL(out), ier);
+  UNPROTECT(1);
+  if (rc) Rf_error("gprc: %s", gprc_last_error());
+  for (long i = 0; i < m; ++i) {
+    if (ier[i] < 0) Rf_error("non-finite function value");
+    if (ier[i] > 0) Rf_error("%s", msg[ier[i] <= 6 ? ier[i] : 6]);
+  }
+  return out;
+}
+
 SEXP C_gprc_gpc_get(SEXP ptr, SEXP what) {
   gprc_gpc* g = (gprc_gpc*)R_ExternalPtrAddr(ptr);
   if (!g) Rf_error("gprc: model handle is NULL");
@@ -214,6 +236,7 @@ static const R_CallMethodDef call_methods[] = {
     {"C_gprc_logml_grad", (DL_FUNC)&C_gprc_logml_grad, 6},
     {"C_gprc_gpc_fit", (DL_FUNC)&C_gprc_gpc_fit, 6},
     {"C_gprc_gpc_predict_latent", (DL_FUNC)&C_gprc_gpc_predict_latent, 4},
+    {"C_gprc_gpc_predict_class", (DL_FUNC)&C_gprc_gpc_predict_class, 2},
     {"C_gprc_gpc_get", (DL_FUNC)&C_gprc_gpc_get, 2},
     {NULL, NULL, 0}};
 

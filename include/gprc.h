@@ -161,6 +161,14 @@ int gprc_gpc_fit_precomputed(gprc_ctx* ctx, const double* K, long n, const doubl
 int gprc_gpc_predict_latent(gprc_gpc* g, const double* Xs, long m, double* fs_bar, double* Vfs);
 int gprc_gpc_predict_latent_precomputed(gprc_gpc* g, const double* Ks, const double* kss, long m, double* fs_bar,
                                         double* Vfs);
+/* GPC$predict_class complete, R/GPCclass.R:108-118: latent mean/variance and, per test point, the reference's
+ * integrate(sigmoid(z) * dnorm(z, fs_bar, sd = Vfs), -Inf, Inf) evaluated on the device by a statement-by-statement
+ * port of QUADPACK dqagi (the routine behind R's integrate(); same tolerances .Machine$double.eps^0.25, 100
+ * subdivisions, same silent ~0 on peaks narrower than its sampling grid).  ier[i] (nullable) is QUADPACK's error
+ * code per point (R stops when it is > 0); -1 flags a non-finite integrand (Vfs <= 0 or NaN). */
+int gprc_gpc_predict_class(gprc_gpc* g, const double* Xs, long m, double* prob, int* ier);
+/* the quadrature alone: out[i] = integral of sigmoid(z) N(z | mean[i], sd[i]) dz  (host arrays, computed on the GPU) */
+int gprc_logistic_gaussian(gprc_ctx* ctx, const double* mean, const double* sd, long m, double* out, int* ier);
 int gprc_gpc_get(gprc_gpc* g, int what, double* host);
 long gprc_gpc_n(const gprc_gpc* g);
 void gprc_gpc_free(gprc_gpc* g);

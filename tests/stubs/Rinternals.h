@@ -39,4 +39,5 @@ void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
+char* R_alloc(size_t, int);
 #endif
