@@ -354,7 +354,12 @@ def main():
             else "gemm_kernel<TrmmNormPolicy> (variance pass v = (L^-1) K_star, fused column norms)"
         roofline = dict(kernel=kname,
                         bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
-                        frac=(achieved / peak_tf) if achieved else None, traffic=None,
+                        frac=(achieved / peak_tf) if achieved else None,
+                        # one ncu --set full capture of a mid-sweep launch of this kernel (profiles/README.md):
+                        # dram__bytes_read + write = 4.95e9 B for a launch whose algorithmic bytes (V rows read once,
+                        # L row panel) are 3.8e9 B
+                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 else None),
+                        traffic_note="bytes of ONE captured launch (grid 148, block row ~197 of 392, 4.37 ms), not per step",
                         peak_source="cuBLAS Dgemm fp64 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json "
                                     "holds no FP64 figure; of measured)",
                         algorithmic_flops_per_step=flops_var, ms_per_step=var_ms,

@@ -1119,19 +1119,27 @@ __global__ void __launch_bounds__(1024) grad_reduce_kernel(int mode, const doubl
     out[0] = (mode == 0) ? 0.5 * t : t;
   }
 }
-// out[0] = sum_{j} sum_{i >= j} W[i + j ld] Z[i + j ld]   (tr(W^T Z) for lower-triangular W); one CTA, fixed order
-__global__ void __launch_bounds__(1024) tril_dot_kernel(const double* __restrict__ W, const double* __restrict__ Z,
-                                                        long ld, long n, double* __restrict__ out) {
-  __shared__ double sh[1024];
+// partial[b] = sum over the columns j = b, b + gridDim.x, ... of sum_{i >= j} W[i + j ld] Z[i + j ld]
+// (tr(W^T Z) for lower-triangular W); the caller adds the partials in a fixed order
+__global__ void __launch_bounds__(256) tril_dot_partial_kernel(const double* __restrict__ W, const double* __restrict__ Z,
+                                                               long ld, long n, double* __restrict__ partial) {
+  __shared__ double sh[256];
   const int tid = threadIdx.x;
   double s = 0.0;
-  for (long j = 0; j < n; ++j)
-    for (long i = j + tid; i < n; i += 1024) s = fma(W[i + j * ld], Z[i + j * ld], s);
+  for (long j = blockIdx.x; j < n; j += gridDim.x)
+    for (long i = j + tid; i < n; i += 256) s = fma(W[i + j * ld], Z[i + j * ld], s);
   sh[tid] = s;
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
-    for (int q = 0; q < 1024; ++q) t += sh[q];
+    for (int q = 0; q < 256; ++q) t += sh[q];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < n; ++q) t += partial[q];
     out[0] = t;
   }
 }
@@ -1165,7 +1173,7 @@ extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* 
     if ((rc = ensure_inverse(c, F))) break;
     if ((rc = dmalloc(&dK0, (size_t)np * np))) break;
     if (nparam > 1 && (rc = dmalloc(&dK1, (size_t)np * np))) break;
-    if ((rc = dmalloc(&vec, (size_t)np * 2)) || (rc = dmalloc(&ones, (size_t)np))) break;
+    if ((rc = dmalloc(&vec, (size_t)np * 2 + 256)) || (rc = dmalloc(&ones, (size_t)np))) break;
     dk_tile_kernel<<<dim3((unsigned)(np / 16), (unsigned)(np / 16)), 256, 0, c->stream>>>(k->id, textbook, v0, v1, g->X,
                                                                                          d, n, np, dK0, dK1);
     c->launches++;
@@ -1185,10 +1193,12 @@ extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* 
         // quad = alpha' dK alpha ; trace = tr(Ky^-1 dK) = tr(W^T (W dK))
         if ((rc = gemv_t(c, dKs[p], np, np, g->alpha, vec))) break;
         grad_reduce_kernel<<<1, 1024, 0, c->stream>>>(1, g->alpha, vec, nullptr, n, c->d_scalars + 8 + p);
-        DgemmPolicy<true> pol{F.W, np, dKs[p], np, Z, np, 1.0, 0.0, (int)np, (int)(np / NB)};
+        // Z = W dK; dK is symmetric, so it is read as its own transpose (both operands stream in 1 KB runs)
+        DgemmPolicy<false> pol{F.W, np, dKs[p], np, Z, np, 1.0, 0.0, (int)np, (int)(np / NB)};
         if ((rc = launch_gemm(c, pol, dim3((unsigned)((np / NB) * (np / NB)))))) break;
-        tril_dot_kernel<<<1, 1024, 0, c->stream>>>(F.W, Z, np, n, c->d_scalars + 16 + p);
-        c->launches += 2;
+        tril_dot_partial_kernel<<<256, 256, 0, c->stream>>>(F.W, Z, np, n, vec + np);
+        sum_partials_kernel<<<1, 32, 0, c->stream>>>(vec + np, 256, c->d_scalars + 16 + p);
+        c->launches += 3;
       }
     }
     if (rc) break;

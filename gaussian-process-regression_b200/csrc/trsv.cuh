@@ -3,6 +3,8 @@
 // here two substitutions), the symmetric GEMV of the GPC Newton step (R/GPCclass.R:82,85) and the reductions behind
 // logp (R/GPRclass.R:153), logq (R/GPCclass.R:103) and fit()'s leading-minor rule (R/fit.R:119).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace gprc {
@@ -105,36 +107,135 @@ __global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Whole substitution sweeps in ONE cooperative launch: the block steps above are latency-bound (n/128 dependent
+// launches of ~10 us of work each); here the grid stays resident and a grid-wide barrier separates the steps.
+// Forward:  every CTA forms x_j = Linv_j b_j itself (128 KB from L2), updates its share of the rows below, sync.
+// Backward: every CTA forms x_j = Linv_j^T b_j, updates its share of the columns left of block j, sync.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trsv_fwd_coop_kernel(const double* __restrict__ L, long ld,
+                                                            const double* __restrict__ dinv, int nt, long n,
+                                                            double* __restrict__ b, double* __restrict__ x) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ double bj[NB], xj[NB], part[NB];
+  const int tid = threadIdx.x, r = tid & (NB - 1), h = tid >> 7;
+  for (int j = 0; j < nt; ++j) {
+    if (tid < NB) bj[tid] = __ldcg(b + (long)j * NB + tid);  // written by other CTAs in the previous step: bypass L1
+    __syncthreads();
+    const double* Li = dinv + (long)j * NB * NB;
+    double s = 0.0, s2 = 0.0;
+#pragma unroll 16
+    for (int c = h * 64; c < h * 64 + 64; c += 2) {
+      s = fma(Li[r + c * NB], bj[c], s);
+      s2 = fma(Li[r + (c + 1) * NB], bj[c + 1], s2);
+    }
+    s += s2;
+    if (h == 1) part[r] = s;
+    __syncthreads();
+    if (h == 0) xj[r] = s + part[r];
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
+    const long first = (long)(j + 1) * NB;
+    for (long row = first + (long)blockIdx.x * 256 + tid; row < n; row += (long)gridDim.x * 256) {
+      const double* Lp = L + row + (long)j * NB * ld;
+      double acc = 0.0, acc2 = 0.0;
+#pragma unroll 16
+      for (int c = 0; c < NB; c += 2) {
+        acc = fma(Lp[(long)c * ld], xj[c], acc);
+        acc2 = fma(Lp[(long)(c + 1) * ld], xj[c + 1], acc2);
+      }
+      b[row] = __ldcg(b + row) - (acc + acc2);
+    }
+    grid.sync();
+  }
+}
+
+__global__ void __launch_bounds__(256) trsv_bwd_coop_kernel(const double* __restrict__ L, long ld,
+                                                            const double* __restrict__ dinv, int nt,
+                                                            double* __restrict__ b, double* __restrict__ x) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ double bj[NB], xj[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gwarp = blockIdx.x * 8 + warp, nwarps = gridDim.x * 8;
+  for (int j = nt - 1; j >= 0; --j) {
+    if (tid < NB) bj[tid] = __ldcg(b + (long)j * NB + tid);
+    __syncthreads();
+    const double* Li = dinv + (long)j * NB * NB;
+    {
+      double s[16];
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp + 8 * rr;
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = lane + 32 * q;
+          acc = fma(Li[c + r * NB], bj[c], acc);
+        }
+        s[rr] = acc;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const double t = warp_sum(s[rr]);
+        if (lane == 0) xj[warp + 8 * rr] = t;
+      }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
+    double xr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xr[q] = xj[lane + 32 * q];
+    const double* Lrow = L + (long)j * NB;
+    const long ncols = (long)j * NB;  // columns left of block j: one warp per column, grid-strided
+    for (long k = gwarp; k < ncols; k += nwarps) {
+      const double* Lp = Lrow + k * ld;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc = fma(Lp[lane + 32 * q], xr[q], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) b[k] = __ldcg(b + k) - acc;
+    }
+    grid.sync();
+    __syncthreads();
+  }
+}
+
+inline int coop_grid(gprc_ctx* ctx, const void* func, long work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long g = (long)ctx->sm_count * (per_sm > 2 ? 2 : per_sm);
+  if (g > work_items) g = work_items;
+  return (int)(g < 1 ? 1 : g);
+}
+
 // x = L^-T L^-1 rhs.  work: n doubles; rhs is left untouched.
 inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
                      double* work, double* tmp, double* x) {
-  const int nt = (int)(n / NB);
+  int nt = (int)(n / NB);
   GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  for (int j = 0; j < nt; ++j) {
-    const long below = n - (long)(j + 1) * NB;
-    const unsigned grid = (unsigned)((below + TRSV_ROWS - 1) / TRSV_ROWS);
-    trsv_fwd_step_kernel<<<grid ? grid : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, n, work, tmp);
+  {
+    const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 255) / 256);
+    void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&n, (void*)&work, (void*)&tmp};
+    GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_fwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
     ctx->launches++;
   }
-  for (int j = nt - 1; j >= 0; --j) {
-    trsv_bwd_step_kernel<<<j ? j : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, tmp, x);
+  {
+    const int grid = coop_grid(ctx, (const void*)trsv_bwd_coop_kernel, (n + 7) / 8);
+    void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&tmp, (void*)&x};
+    GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_bwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
     ctx->launches++;
   }
-  GPRC_CUDA(cudaGetLastError());
   return 0;
 }
 // only the forward half: x = L^-1 rhs
 inline int trsv_forward(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
                         double* work, double* x) {
-  const int nt = (int)(n / NB);
+  int nt = (int)(n / NB);
   GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  for (int j = 0; j < nt; ++j) {
-    const long below = n - (long)(j + 1) * NB;
-    const unsigned grid = (unsigned)((below + TRSV_ROWS - 1) / TRSV_ROWS);
-    trsv_fwd_step_kernel<<<grid ? grid : 1, 256, 0, ctx->stream>>>(L, ld, dinv, j, n, work, x);
-    ctx->launches++;
-  }
-  GPRC_CUDA(cudaGetLastError());
+  const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 255) / 256);
+  void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&n, (void*)&work, (void*)&x};
+  GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_fwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
   return 0;
 }
 
