@@ -8,6 +8,7 @@
 // column sums that give the predictive mean t(K_star) %*% alpha (R/GPRclass.R:161) without re-reading K_star.
 #pragma once
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace gprc {
 
@@ -205,7 +206,167 @@ __global__ void cov_pointwise_kernel(const KSpecDev k, const double* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core build (north_star subsystem 1): the d-dimensional contraction G = A^T B of a 64 x 64 tile runs on
+// the FP64 tensor cores (DMMA m8n8k4 straight from the point tiles, which the TMA engine drops into shared memory
+// with ONE bulk copy each: a tile of 64 points x d is contiguous in the reference's d x n layout); the epilogue
+// turns G into squared distances r2 = |a|^2 + |b|^2 - 2 G (clamped at 0, exactly 0 on the diagonal of K(X, X)) or
+// uses it as the dot product, applies the kernel, adds the noise on the diagonal in-register and stores the tile.
+// Eligible: sqrexp / rationalquadratic / polynomial / linear with d a multiple of 4 (4..32); see cov_uses_gram for
+// when it is actually chosen.  gammaexp always keeps the direct differences (its sqrt amplifies the cancellation error
+// of the expansion near coincident points).  The expansion perturbs r2 by ~1e-16 (|a|^2 + |b|^2), i.e. kernel
+// entries by ~1e-15 relative -- three orders below what the Cholesky of K + noise I itself commits.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GT = 64;         // tensor-core build tile (same 64 x 64 granularity as the direct build)
+constexpr int GRAM_THREADS = 128;  // 4 warps as 2 x 2, each a 32 x 32 block of 4 x 4 m8n8k4 accumulators (64 registers)
+constexpr int GRAM_DMAX = 32;
+inline size_t gram_smem_bytes(int d) { return (size_t)(2 * GT * d + 2 * GT + 2 * GT) * 8 + 64; }
+
+template <int FAMILY>
+__global__ void __launch_bounds__(GRAM_THREADS, 4) cov_gram_kernel(const CovParams p) {
+  extern __shared__ __align__(128) unsigned char graw[];
+  const int D = p.d, tid = threadIdx.x;
+  double* As = reinterpret_cast<double*>(graw);  // [GT][D], point-major (K-major for the DMMA fragments)
+  double* Bs = As + GT * D;
+  double* na = Bs + GT * D;
+  double* nbv = na + GT;
+  double* red = nbv + GT;  // [2][GT]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * GT);
+  const long ti = blockIdx.x, tj = blockIdx.y;
+  if (p.lower_only && tj * GT + p.col_offset > ti * GT + (GT - 1)) return;
+  const long i0 = ti * GT, j0 = tj * GT;
+  const int validA = (int)max(0L, min((long)GT, p.nA - i0)), validB = (int)max(0L, min((long)GT, p.nB - j0));
+  if (tid == 0) {
+    mbar_init(smem_u32(bar), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytesA = (uint32_t)validA * D * 8, bytesB = (uint32_t)validB * D * 8;
+    mbar_arrive_expect_tx(smem_u32(bar), bytesA + bytesB);
+    if (bytesA) bulk_g2s(smem_u32(As), p.A + i0 * D, bytesA, smem_u32(bar));
+    if (bytesB) bulk_g2s(smem_u32(Bs), p.B + j0 * D, bytesB, smem_u32(bar));
+  }
+  for (int e = validA * D + tid; e < GT * D; e += GRAM_THREADS) As[e] = 0.0;  // points beyond the matrix: zero rows
+  for (int e = validB * D + tid; e < GT * D; e += GRAM_THREADS) Bs[e] = 0.0;
+  mbar_wait(smem_u32(bar), 0);
+  __syncthreads();
+  if (FAMILY == FAM_DOT && p.k.id == GPRC_LINEAR) {
+    for (int e = tid; e < GT * D; e += GRAM_THREADS) As[e] = linear_sigma(p.k, e % D) * As[e];  // (sigma * x) * y
+    __syncthreads();
+  }
+  if (FAMILY == FAM_DIST) {
+    const double* src = (tid < GT) ? As + tid * D : Bs + (tid - GT) * D;
+    double s = 0.0;
+    for (int dd = 0; dd < D; ++dd) s = fma(src[dd], src[dd], s);
+    (tid < GT ? na : nbv)[tid & (GT - 1)] = s;
+    __syncthreads();
+  }
+  const int lane = tid & 31, warp = tid >> 5, warp_m = warp & 1, warp_n = warp >> 1;
+  const int lk = lane & 3, lr = lane >> 2;
+  double acc[4][4][2];
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+  for (int k0 = 0; k0 < D; k0 += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) a[mb] = As[(warp_m * 32 + mb * 8 + lr) * D + k0 + lk];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) b[nb] = Bs[(warp_n * 32 + nb * 8 + lr) * D + k0 + lk];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+  }
+  double rsum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int cl = warp_n * 32 + nb * 8 + 2 * lk + r;
+      const long gj = j0 + cl;
+      const double cw = (p.colweights && gj < p.nB) ? p.colweights[gj] : 0.0;
+      const double cs = (p.colscale && gj < p.nB) ? p.colscale[gj] : 1.0;
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        const int rl = warp_m * 32 + mb * 8 + lr;
+        const long gi = i0 + rl;
+        double v;
+        if (gi < p.nA && gj < p.nB) {
+          if (FAMILY == FAM_DIST) {
+            double r2 = (na[rl] + nbv[cl]) - 2.0 * acc[mb][nb][r];
+            r2 = fmax(r2, 0.0);
+            if (p.symmetric && gi == gj + p.col_offset) r2 = 0.0;
+            v = kfun_dist(p.k, r2);
+          } else {
+            v = kfun_dot(p.k, acc[mb][nb][r]);
+          }
+          if (p.symmetric && gi == gj + p.col_offset) v += p.diag_add;
+          rsum[mb] = fma(v, cw, rsum[mb]);
+          v *= cs;
+        } else {
+          v = (p.pad_identity && gi == gj + p.col_offset) ? 1.0 : 0.0;
+        }
+        if (gi < p.rows_pad && gj < p.cols_pad) p.out[gi + gj * p.ldo] = v;
+      }
+    }
+  if (p.colweights) {
+    // pmean[tile_j][i] = sum over the tile's 64 columns: the lanes of a quad, then the two column warps
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      double s = rsum[mb];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (lk == 0) red[warp_n * GT + warp_m * 32 + mb * 8 + lr] = s;
+    }
+    __syncthreads();
+    if (tid < GT) {
+      const long gi = i0 + tid;
+      if (gi < p.rows_pad) p.pmean[tj * p.ldpm + gi] = red[tid] + red[GT + tid];
+    }
+  }
+}
+
+// which build serves these parameters (callers need the tile height to size the mean partials)
+// GPRC_OPT_GRAM_DMMA: 0 never, 2 wherever eligible, 1 (default) where it measured faster on B200: the build is bound
+// by the FP64 exp / pow / division of the epilogue, not by the d-dimensional contraction, so the tensor-core path only
+// pays for the dot-product kernels from d = 12 (n = 16 384, lower triangle, ms: sqrexp d=8 1.14 vs 0.99 direct,
+// d=32 1.72 vs 1.57; polynomial d=12 1.61 vs 1.64, d=16 1.65 vs 1.71, d=32 1.76 vs 2.08).
+inline bool cov_uses_gram(const gprc_ctx* ctx, const CovParams& p) {
+  const int fam = kernel_family(p.k.id);
+  const bool eligible = (fam == FAM_DOT || (fam == FAM_DIST && p.k.id != GPRC_GAMMAEXP)) && p.d >= 4 &&
+                        p.d <= GRAM_DMAX && p.d % 4 == 0 && !p.rowscale && !p.weights && p.rows_pad % GT == 0 &&
+                        p.cols_pad % GT == 0;
+  if (!eligible || ctx->opt_gram_dmma == 0) return false;
+  if (ctx->opt_gram_dmma >= 2) return true;
+  return fam == FAM_DOT && p.d >= 12;
+}
+inline int cov_tile_rows(const gprc_ctx* ctx, const CovParams& p) { return cov_uses_gram(ctx, p) ? GT : CT; }
+
 inline int launch_cov(gprc_ctx* ctx, const CovParams& p) {
+  if (cov_uses_gram(ctx, p)) {
+    dim3 g((unsigned)(p.rows_pad / GT), (unsigned)(p.cols_pad / GT));
+    if (g.x == 0 || g.y == 0) return 0;
+    if (g.y > 65535) return set_error(-1, __FILE__, __LINE__, "cov tile grid too wide: chunk the columns");
+    static bool configured[64] = {false};
+    if (!configured[ctx->device & 63]) {
+      GPRC_CUDA(cudaFuncSetAttribute(cov_gram_kernel<FAM_DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)gram_smem_bytes(GRAM_DMAX)));
+      GPRC_CUDA(cudaFuncSetAttribute(cov_gram_kernel<FAM_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)gram_smem_bytes(GRAM_DMAX)));
+      configured[ctx->device & 63] = true;
+    }
+    const size_t smem = gram_smem_bytes(p.d);
+    if (kernel_family(p.k.id) == FAM_DIST)
+      cov_gram_kernel<FAM_DIST><<<g, GRAM_THREADS, smem, ctx->stream>>>(p);
+    else
+      cov_gram_kernel<FAM_DOT><<<g, GRAM_THREADS, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    GPRC_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((unsigned)(p.rows_pad / CT), (unsigned)(p.cols_pad / CT));
   if (grid.x == 0 || grid.y == 0) return 0;
   if (grid.y > 65535) return set_error(-1, __FILE__, __LINE__, "cov tile grid too wide: chunk the columns");

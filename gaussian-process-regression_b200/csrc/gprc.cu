@@ -442,7 +442,7 @@ static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d
                          double* out, long ldo, long rows_pad, long cols_pad, bool lower_only, bool symmetric,
                          double diag_add, bool pad_identity, const double* rowscale, const double* weights,
                          double* pmean, long ldpm, const double* colscale = nullptr,
-                         const double* colweights = nullptr) {
+                         const double* colweights = nullptr, int* tile_rows = nullptr) {
   CovParams p;
   p.k = k;
   p.A = dA;
@@ -465,6 +465,7 @@ static int cov_build_dev(gprc_ctx* c, const KSpecDev& k, const double* dA, int d
   p.colscale = colscale;
   p.colweights = colweights;
   p.col_offset = 0;
+  if (tile_rows) *tile_rows = cov_tile_rows(c, p);
   return launch_cov(c, p);
 }
 
@@ -476,9 +477,9 @@ extern "C" int gprc_cov_matrix(gprc_ctx* c, const gprc_kernel* k, const double* 
   SpecHolder spec;
   GPRC_CHECK(make_spec(c, k, d, spec));
   double *dA = nullptr, *dB = nullptr, *dout = nullptr;
-  const long rp = round_up(nA, CT);
+  const long rp = round_up(nA, NB);
   // column chunks bound the device buffer (<= 2 GiB) and the grid's y extent
-  long cchunk = std::max<long>(CT, std::min<long>(round_up(nB, CT), ((2L << 30) / 8 / rp) / CT * CT));
+  long cchunk = std::max<long>(NB, std::min<long>(round_up(nB, NB), ((2L << 30) / 8 / rp) / NB * NB));
   cchunk = std::min<long>(cchunk, 65535L * CT);
   int rc = 0;
   do {
@@ -491,7 +492,7 @@ extern "C" int gprc_cov_matrix(gprc_ctx* c, const gprc_kernel* k, const double* 
       const long nc = std::min(cchunk, nB - c0);
       {
         PhaseTimer t(c, GPRC_T_BUILD_K);
-        rc = cov_build_dev(c, spec.dev, dA, d, nA, dB + c0 * d, nc, dout, rp, rp, round_up(nc, CT), false, false, 0.0,
+        rc = cov_build_dev(c, spec.dev, dA, d, nA, dB + c0 * d, nc, dout, rp, rp, round_up(nc, NB), false, false, 0.0,
                            false, nullptr, nullptr, nullptr, 0);
       }
       if (rc) break;
@@ -645,6 +646,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   const bool use_trsm = (c->opt_predict_path == 2) || (c->opt_predict_path == 0 && !F.W && m >= WAVE_COLS);
   if (!use_trsm) GPRC_CHECK(ensure_inverse(c, F));
   GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
+  int mean_tile = CT;  // columns (training points) per partial of the mean: 64 (direct build) or 128 (tensor-core build)
   for (long c0 = 0; c0 < m; c0 += ws.mc) {
     const long mcur = std::min(ws.mc, m - c0);
     const long mpad = round_up(mcur, NB);
@@ -653,7 +655,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
       // K_star^T tile by tile: rows = test points, columns = training points; sqrt(W) scaling and the mean's
       // weighted sums run along the training axis
       GPRC_CHECK(cov_build_dev(c, k, dXs + c0 * d, d, mcur, dX, F.n, ws.Ks, ws.mc, mpad, F.n_pad, false, false, 0.0,
-                               false, nullptr, nullptr, ws.pmean, ws.mc, rowscale, weights));
+                               false, nullptr, nullptr, ws.pmean, ws.mc, rowscale, weights, &mean_tile));
       cov_pointwise_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(k, dXs + c0 * d, dXs + c0 * d, d,
                                                                                  mcur, ws.kss);
       c->launches++;
@@ -663,7 +665,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     else
       GPRC_CHECK(variance_pass(c, F, ws, mpad, nullptr, 0));
     finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
-        ws.pmean, ws.mc, (int)(F.n_pad / CT), ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, dmean + c0,
+        ws.pmean, ws.mc, (int)(F.n_pad / mean_tile), ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, dmean + c0,
         dvar + c0);
     c->launches++;
     GPRC_CUDA(cudaGetLastError());
@@ -909,6 +911,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
   FactorState& F = g->F;
   const long mp = round_up(m, NB);
   GPRC_CHECK(ensure_inverse(c, F));
+  int mean_tile = CT;
   PredictWorkspace ws;  // private workspace sized for the whole set (V^T must be complete before the product)
   double *dXs = nullptr, *dmean = nullptr, *dVt = nullptr, *dS = nullptr;
   int rc = 0;
@@ -926,7 +929,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
     {
       PhaseTimer t(c, GPRC_T_BUILD_KS);
       if ((rc = cov_build_dev(c, g->spec.dev, dXs, g->d, m, g->X, F.n, ws.Ks, mp, mp, F.n_pad, false, false, 0.0,
-                              false, nullptr, nullptr, ws.pmean, ws.mc, nullptr, g->alpha)))
+                              false, nullptr, nullptr, ws.pmean, ws.mc, nullptr, g->alpha, &mean_tile)))
         break;
       // Sigma starts as covariance_matrix(X_star, X_star, k); zero padding
       if ((rc = cov_build_dev(c, g->spec.dev, dXs, g->d, m, dXs, m, dS, mp, mp, mp, false, false, 0.0, false, nullptr,
@@ -935,7 +938,7 @@ extern "C" int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, doubl
     }
     if ((rc = variance_pass(c, F, ws, mp, dVt, mp))) break;
     finalize_predict_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(
-        ws.pmean, ws.mc, (int)(F.n_pad / CT), nullptr, 0, 0, nullptr, m, dmean, nullptr);
+        ws.pmean, ws.mc, (int)(F.n_pad / mean_tile), nullptr, 0, 0, nullptr, m, dmean, nullptr);
     c->launches++;
     {
       // Sigma -= V^T V  with V^T stored m_pad x n_pad (test point contiguous): C = C - A A^T

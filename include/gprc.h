@@ -48,8 +48,11 @@ typedef struct {
 
 /* flags for gprc_ctx_set_option */
 enum {
-  GPRC_OPT_GRAM_DMMA = 1, /* reserved: FP64 tensor-core Gram-tile build (not implemented; builds use direct
-                             differences exactly as R/GPRclass.R:394 writes them) */
+  GPRC_OPT_GRAM_DMMA = 1, /* kernel-matrix build on the FP64 tensor cores (TMA-fed 64 x 64 tiles, X^T Y by DMMA, norm
+                             expansion for distances; eligible: sqrexp / rationalquadratic / polynomial / linear, d a
+                             multiple of 4 in 4..32).  0: never (direct differences exactly as R/GPRclass.R:394 writes
+                             them); 1 (default): where it measured faster (dot-product kernels, d >= 12); 2: wherever
+                             eligible */
   GPRC_OPT_PREDICT_PATH = 2 /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
                                (one launch per chunk; best for repeated / small predicts), 2 blocked substitution
                                (no n^3/3 inversion; chosen automatically for >= 18 944 test points) */

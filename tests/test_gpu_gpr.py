@@ -227,3 +227,24 @@ def test_linear_kernel_with_per_dimension_sigma(gprc, oracle):
     assert_mean_var(g.predict(Xs), o.predict(Xs), np.abs(ok(Xs, Xs)))
     with pytest.raises(ValueError):
         gprc.GPR.linear.new(X, y, 0.2, np.array([1.0, 2.0]))  # stopifnot(length(sigma) == nrow(X))
+
+
+@pytest.mark.parametrize("name,params,noise", [("sqrexp", dict(l=1.0), 0.01), ("rationalquadratic", dict(l=1.0, alpha=1.0), 0.05),
+                                               ("polynomial", dict(sigma=1.0, p=3.0), 0.1)])
+def test_gpr_with_tensor_core_build_matches_oracle(gprc, oracle, ctx, name, params, noise):
+    """End-to-end tolerance with K and K_star built by the DMMA Gram-tile kernel (norm expansion)."""
+    rng = np.random.default_rng(51)
+    X = rng.uniform(-1, 1, (8, 600))
+    y = np.sum(np.sin(np.pi * X), axis=0) + rng.normal(0, 0.1, 600)
+    Xs = rng.uniform(-1, 1, (8, 333))
+    Xs[:, 0] = X[:, 0]
+    ctx.set_option(gprc._lib.OPT_GRAM_DMMA, 2)
+    try:
+        g = gprc.GPR(X, y, noise, gprc.cov_func(getattr(gprc, name), **params), ctx=ctx)
+        got = g.predict(Xs)
+    finally:
+        ctx.set_option(gprc._lib.OPT_GRAM_DMMA, 1)
+    ok = oracle.cov_func(getattr(oracle, name), **params)
+    o = oracle.GPR(X, y, noise, ok)
+    assert abs(g.logp[0, 0] - o.logp) <= LOGP_RTOL * abs(o.logp)
+    assert_mean_var(got, o.predict(Xs), ok(Xs, Xs))

@@ -94,6 +94,25 @@ KERNELS = [
 @pytest.mark.parametrize("name,params", KERNELS)
 @pytest.mark.parametrize("D,nA,nB", [(1, 5, 3), (2, 70, 129), (8, 257, 64), (11, 33, 200)])
 def test_cov_matrix_matches_oracle(gprc, oracle, ctx, name, params, D, nA, nB):
+    _cov_matrix_case(gprc, oracle, ctx, name, params, D, nA, nB, gram=1)
+
+
+@pytest.mark.parametrize("name,params", [k for k in KERNELS if k[0] in ("linear", "polynomial", "sqrexp", "rationalquadratic")])
+@pytest.mark.parametrize("D,nA,nB", [(4, 70, 129), (8, 257, 64), (16, 130, 200), (32, 64, 65)])
+def test_cov_matrix_tensor_core_build(gprc, oracle, ctx, name, params, D, nA, nB):
+    # GPRC_OPT_GRAM_DMMA = 2: the DMMA Gram-tile build wherever it is eligible
+    _cov_matrix_case(gprc, oracle, ctx, name, params, D, nA, nB, gram=2)
+
+
+def _cov_matrix_case(gprc, oracle, ctx, name, params, D, nA, nB, gram):
+    ctx.set_option(gprc._lib.OPT_GRAM_DMMA, gram)
+    try:
+        _cov_matrix_check(gprc, oracle, ctx, name, params, D, nA, nB, gram)
+    finally:
+        ctx.set_option(gprc._lib.OPT_GRAM_DMMA, 1)
+
+
+def _cov_matrix_check(gprc, oracle, ctx, name, params, D, nA, nB, gram):
     rng = np.random.default_rng(D * 1000 + nA + nB)
     A = rng.uniform(-1, 1, (D, nA))
     B = rng.uniform(-1, 1, (D, nB))
@@ -105,7 +124,30 @@ def test_cov_matrix_matches_oracle(gprc, oracle, ctx, name, params, D, nA, nB):
     # dot-product kernels: NumPy's reduction order differs, so a dot near zero only agrees to a few ulp of
     # sum_d |x_d y_d| (<= D here), which the polynomial epilogue scales by p (sigma + D)^(p-1)
     atol = 0.0 if name in ("sqrexp", "gammaexp", "rationalquadratic", "constant") else 4e-16 * D * 64
+    rtol = 1e-14
+    if gram == 2 and D % 4 == 0 and name in ("sqrexp", "rationalquadratic"):
+        # tensor-core build: r2 = |a|^2 + |b|^2 - 2 a.b carries ~1e-16 (|a|^2 + |b|^2) of cancellation error,
+        # i.e. ~1e-15..1e-14 relative on the entry (exactly 1 at coincident points is NOT guaranteed off the diagonal)
+        rtol = 2e-13
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name,params", [k for k in KERNELS if k[0] != "constant"])
+def test_cov_matrix_direct_build_is_faithful_to_1e14(gprc, oracle, ctx, name, params):
+    # GPRC_OPT_GRAM_DMMA = 0: every kernel goes through direct differences in the reference's operation order
+    rng = np.random.default_rng(77)
+    A, B = rng.uniform(-1, 1, (8, 200)), rng.uniform(-1, 1, (8, 130))
+    B[:, 3] = A[:, 5]
+    ctx.set_option(gprc._lib.OPT_GRAM_DMMA, 0)
+    try:
+        got = gprc.covariance_matrix(A, B, gprc.cov_func(getattr(gprc, name), **params), ctx=ctx)
+    finally:
+        ctx.set_option(gprc._lib.OPT_GRAM_DMMA, 1)
+    ref = oracle.covariance_matrix(A, B, oracle.cov_func(getattr(oracle, name), **params))
+    atol = 0.0 if name in ("sqrexp", "gammaexp", "rationalquadratic") else 4e-16 * 8 * 64
     np.testing.assert_allclose(got, ref, rtol=1e-14, atol=atol)
+    if name in ("sqrexp", "gammaexp", "rationalquadratic"):
+        assert got[5, 3] == 1.0  # coincident points: exactly k(x, x)
 
 
 def test_cov_matrix_linear_vector_sigma(gprc, oracle, ctx):
