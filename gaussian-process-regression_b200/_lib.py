@@ -155,11 +155,8 @@ class Context:
             self.lib.gprc_ctx_free(self.handle)
             self.handle = None
 
-    def __del__(self):  # pragma: no cover
-        try:
-            self.close()
-        except Exception:
-            pass
+    # no __del__: at interpreter shutdown a context could be collected before the models that still point into it;
+    # contexts live until close() is called explicitly or the process ends
 
     def set_option(self, option, value):
         check(self.lib.gprc_ctx_set_option(self.handle, option, int(value)))

@@ -80,7 +80,7 @@ class GPC:
 
     def __del__(self):  # pragma: no cover
         try:
-            if getattr(self, "_handle", None):
+            if getattr(self, "_handle", None) and getattr(self._ctx, "handle", None):
                 self._ctx.lib.gprc_gpc_free(self._handle)
                 self._handle = None
         except Exception:

@@ -102,7 +102,7 @@ class GPR:
 
     def __del__(self):  # pragma: no cover
         try:
-            if getattr(self, "_handle", None):
+            if getattr(self, "_handle", None) and getattr(self._ctx, "handle", None):
                 self._ctx.lib.gprc_gpr_free(self._handle)
                 self._handle = None
         except Exception:
