@@ -143,3 +143,22 @@ def test_fit_matches_oracle_on_test_fit_R(gprc, oracle):
             assert r["cov"] == expected[i]
         np.testing.assert_allclose(r["score"], ro["score"], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(r["par"], ro["par"], rtol=1e-4)
+
+
+def test_gpc_and_dens_match_committed_golden_vectors(gprc):
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+    g = gprc.GPC(G["gpc_X"], G["gpc_y"], gprc.cov_func(gprc.sqrexp, l=float(G["gpc_l"])), verbose=False)
+    assert g.iterations == int(G["gpc_iter"])
+    np.testing.assert_allclose(g.objective_trace, G["gpc_trace"], rtol=1e-9)
+    np.testing.assert_allclose(g.f_hat, G["gpc_f_hat"], rtol=0, atol=1e-9 * np.max(np.abs(G["gpc_f_hat"])))
+    assert abs(g.logq - float(G["gpc_logq"])) <= 1e-8 * abs(float(G["gpc_logq"]))
+    fs, V = g.predict_latent(G["gpc_Xs"])
+    np.testing.assert_allclose(fs, G["gpc_fs_bar"], rtol=0, atol=1e-9 * np.max(np.abs(G["gpc_fs_bar"])))
+    np.testing.assert_allclose(V, G["gpc_Vfs"], rtol=0, atol=1e-9)
+    prob = g.predict_class(G["gpc_Xs"])
+    assert np.array_equal(prob >= 0.5, G["gpc_prob"] >= 0.5)
+    np.testing.assert_allclose(prob, G["gpc_prob"], rtol=1e-7, atol=1e-10)
+    obj = gprc.Objective(G["dens_X"], G["dens_y"], 0.05, minors="cholesky")
+    got = [obj.dens("rationalquadratic", list(t)) for t in G["dens_thetas"]]
+    np.testing.assert_allclose(got, G["dens_rq"], rtol=1e-8)

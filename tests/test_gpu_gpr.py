@@ -248,3 +248,21 @@ def test_gpr_with_tensor_core_build_matches_oracle(gprc, oracle, ctx, name, para
     o = oracle.GPR(X, y, noise, ok)
     assert abs(g.logp[0, 0] - o.logp) <= LOGP_RTOL * abs(o.logp)
     assert_mean_var(got, o.predict(Xs), ok(Xs, Xs))
+
+
+GOLD = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+@pytest.mark.parametrize("tag", ["c1", "c4s", "rq", "gx", "poly"])
+def test_gpu_path_matches_committed_golden_vectors(gprc, tag):
+    """The CUDA path against the committed snapshot (tests/golden/golden_v1.npz), independent of the live oracle."""
+    import json
+    name = str(GOLD[tag + "_kernel"])
+    params = json.loads(str(GOLD[tag + "_params"]))
+    g = gprc.GPR(GOLD[tag + "_X"], GOLD[tag + "_y"], float(GOLD[tag + "_noise"]), gprc.cov_func(getattr(gprc, name), **params))
+    ref = GOLD[tag + "_pred"]
+    got = g.predict(GOLD[tag + "_Xs"])
+    kss = np.asarray(gprc.cov_func(getattr(gprc, name), **params)(GOLD[tag + "_Xs"], GOLD[tag + "_Xs"]))
+    assert_mean_var(got, ref, np.abs(kss))
+    assert abs(g.logp[0, 0] - float(GOLD[tag + "_logp"])) <= LOGP_RTOL * abs(float(GOLD[tag + "_logp"]))
+    np.testing.assert_allclose(g.alpha, GOLD[tag + "_alpha"], rtol=0, atol=1e-8 * np.max(np.abs(GOLD[tag + "_alpha"])))
