@@ -87,6 +87,7 @@ SIGNATURES = {
     "gprc_gpc_get": (C.c_int, [_P, C.c_int, c_double_p]),
     "gprc_gpc_n": (C.c_long, [_P]),
     "gprc_gpc_free": (None, [_P]),
+    "gprc_mvn_sample": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, C.c_long, c_double_p, c_long_p]),
     "gprc_dist_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "gprc_dist_create": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(_P)]),
     "gprc_dist_free": (None, [_P]),

@@ -1573,6 +1573,63 @@ extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, co
 }
 
 // =================================================================================================================
+// posterior sampling helper: multivariate_normal(), R/GPRclass.R:360-370
+// =================================================================================================================
+namespace gprc {
+// zero everything strictly above the diagonal (the uploaded covariance had both triangles)
+__global__ void tril_inplace_kernel(double* __restrict__ M, long ld, long n) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long j = blockIdx.y;
+  if (i < n && j < n && i < j) M[i + j * ld] = 0.0;
+}
+__global__ void add_mean_kernel(double* __restrict__ out, long ld, long m, long ns, const double* __restrict__ mean) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long j = blockIdx.y;
+  if (i < m && j < ns) out[i + j * ld] += mean[i];
+}
+}  // namespace gprc
+
+extern "C" int gprc_mvn_sample(gprc_ctx* c, const double* mean, const double* cov, long m, const double* Z, long ns,
+                               double* out, long* info) {
+  GPRC_ARG(c && mean && cov && Z && out && info && m > 0 && ns > 0);
+  DeviceGuard guard(c);
+  FactorState F;
+  double *dZ = nullptr, *dout = nullptr, *dmean = nullptr;
+  const long sp = round_up(ns, NB);
+  int rc = 0;
+  *info = 0;
+  do {
+    if ((rc = factor_alloc(F, m))) break;
+    const long mp = F.n_pad;
+    if ((rc = dmalloc(&dZ, (size_t)mp * sp)) || (rc = dmalloc(&dout, (size_t)mp * sp)) || (rc = dmalloc(&dmean, (size_t)m)))
+      break;
+    if ((rc = upload_square_padded(c, cov, m, F.L, mp, 0.0, true))) break;
+    if ((rc = factor_run(c, F, info))) break;
+    if (*info != 0) break;  // the caller falls back to eigen(), as the reference does
+    cudaMemsetAsync(dZ, 0, sizeof(double) * mp * sp, c->stream);
+    cudaMemcpy2DAsync(dZ, mp * sizeof(double), Z, m * sizeof(double), m * sizeof(double), ns, cudaMemcpyHostToDevice,
+                      c->stream);
+    cudaMemcpyAsync(dmean, mean, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream);
+    tril_inplace_kernel<<<grid2(mp, mp), 256, 0, c->stream>>>(F.L, mp, mp);
+    c->launches++;
+    DgemmPolicy<true> pol{F.L, mp, dZ, mp, dout, mp, 1.0, 0.0, (int)mp, (int)(mp / NB)};  // L %*% Z
+    if ((rc = launch_gemm(c, pol, dim3((unsigned)((mp / NB) * (sp / NB)))))) break;
+    add_mean_kernel<<<grid2(m, ns), 256, 0, c->stream>>>(dout, mp, m, ns, dmean);
+    c->launches++;
+    cudaMemcpy2DAsync(out, m * sizeof(double), dout, mp * sizeof(double), m * sizeof(double), ns, cudaMemcpyDeviceToHost,
+                      c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  F.release();
+  dfree(dZ);
+  dfree(dout);
+  dfree(dmean);
+  return rc;
+}
+
+// =================================================================================================================
 // multi-GPU Cholesky + solve (dist.cuh)
 // =================================================================================================================
 #include "dist.cuh"

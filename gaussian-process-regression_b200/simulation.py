@@ -44,15 +44,25 @@ def multivariate_normal(n, mean, covariance, tol=1e-6, rng=None):
     covariance = np.asarray(covariance, float)
     if len(mean) != covariance.shape[0]:
         raise ValueError("length(mean) == nrow(covariance) is not TRUE")
-    try:
-        L = np.linalg.cholesky(covariance)
-    except np.linalg.LinAlgError:
-        w, V = np.linalg.eigh(covariance)
-        w, V = w[::-1], V[:, ::-1]
-        if not np.all(w > -tol * abs(w[0])):
-            raise ValueError("all(eigval > -tol * abs(eigval[1])) is not TRUE")
-        L = V @ np.diag(np.sqrt(np.maximum(w, 0)))
-    return mean[:, None] + L @ rng.standard_normal((len(mean), n))
+    import ctypes as C
+    from . import _lib
+    m = len(mean)
+    Z = np.asfortranarray(rng.standard_normal((m, n)))  # the normals are the caller's (R: rnorm)
+    ctx = _lib.default_context()
+    out = np.empty((m, n), order="F")
+    info = C.c_long(0)
+    _lib.check(ctx.lib.gprc_mvn_sample(ctx.handle, _lib.dptr(np.ascontiguousarray(mean)),
+                                       _lib.dptr(np.asfortranarray(covariance)), m, _lib.dptr(Z), n, _lib.dptr(out),
+                                       C.byref(info)))
+    if info.value == 0:
+        return out
+    # chol() failed: the reference's eigen fallback (R/GPRclass.R:363-368) -- host code in the reference as well
+    w, V = np.linalg.eigh(covariance)
+    w, V = w[::-1], V[:, ::-1]
+    if not np.all(w > -tol * abs(w[0])):
+        raise ValueError("all(eigval > -tol * abs(eigval[1])) is not TRUE")
+    L = V @ np.diag(np.sqrt(np.maximum(w, 0)))
+    return mean[:, None] + L @ Z
 
 
 def simulate_regression(func, limits, training_points=None, training_size=10, observation_noise=lambda X: 0.0,

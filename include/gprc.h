@@ -176,6 +176,13 @@ int gprc_gpc_get(gprc_gpc* g, int what, double* host);
 long gprc_gpc_n(const gprc_gpc* g);
 void gprc_gpc_free(gprc_gpc* g);
 
+/* ---- posterior sampling helper ------------------------------------------------------------- */
+/* multivariate_normal(n, mean, covariance), R/GPRclass.R:360-370: out (m x ns) = mean + t(chol(covariance)) %*% Z with
+ * Z (m x ns) standard normals drawn by the caller (R's rnorm stream stays R's).  info > 0: chol() failed and nothing is
+ * written -- the host then runs the reference's eigen fallback (R/GPRclass.R:363-368). */
+int gprc_mvn_sample(gprc_ctx* ctx, const double* mean, const double* cov, long m, const double* Z, long ns, double* out,
+                    long* info);
+
 /* ---- multi-GPU: Cholesky + solve for n beyond one GPU (BASELINE config 5) ------------------------ */
 /* One process per GPU.  K + noise I is distributed by outer panels of 512 columns (panel p on rank p mod world) and
  * factored right-looking with panel broadcasts over NCCL (bound at run time with dlopen).  Replaces, collectively,

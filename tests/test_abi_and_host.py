@@ -129,8 +129,21 @@ def test_simulation_helpers(gprc, oracle):
     np.testing.assert_array_equal(gprc.combine_all([[1.0, 2.0], [3.0, 4.0, 5.0]]), oracle.combine_all([[1.0, 2.0], [3.0, 4.0, 5.0]]))
     noise = gprc.iid_noise(lambda n, sd: np.full(n, sd), sd=0.1)
     np.testing.assert_array_equal(noise(np.zeros((3, 5))), np.full(5, 0.1))
-    z = gprc.multivariate_normal(4, [0.0, 1.0], np.array([[1.0, 0.5], [0.5, 1.0]]), rng=np.random.default_rng(0))
-    assert z.shape == (2, 4)
+
+
+@pytest.mark.gpu
+def test_multivariate_normal(gprc):
+    # mean + t(chol(Sigma)) %*% Z on the device; singular Sigma takes the reference's eigen fallback (R/GPRclass.R:363-368)
+    cov = np.array([[1.0, 0.5], [0.5, 1.0]])
+    z = gprc.multivariate_normal(4, [0.0, 1.0], cov, rng=np.random.default_rng(0))
+    Z = np.random.default_rng(0).standard_normal((2, 4))
+    np.testing.assert_allclose(z, np.array([[0.0], [1.0]]) + np.linalg.cholesky(cov) @ Z, rtol=1e-13, atol=1e-14)
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((300, 300))
+    S = G @ G.T / 300 + 0.1 * np.eye(300)
+    z = gprc.multivariate_normal(7, np.arange(300.0), S, rng=np.random.default_rng(1))
+    Z = np.random.default_rng(1).standard_normal((300, 7))
+    np.testing.assert_allclose(z, np.arange(300.0)[:, None] + np.linalg.cholesky(S) @ Z, rtol=1e-10, atol=1e-10)
     z = gprc.multivariate_normal(3, [0.0, 0.0], np.ones((2, 2)), rng=np.random.default_rng(0))  # singular: eigen path
     np.testing.assert_allclose(z[0], z[1], atol=1e-7)
 
