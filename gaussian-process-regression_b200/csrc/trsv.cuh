@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) trsv_fwd_coop_kernel(const double* __rest
                                                             const double* __restrict__ dinv, int nt, long n,
                                                             double* __restrict__ b, double* __restrict__ x) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  __shared__ double bj[NB], xj[NB], part[NB];
+  __shared__ double bj[NB], xj[NB], part[NB], quart[256];
   const int tid = threadIdx.x, r = tid & (NB - 1), h = tid >> 7;
   for (int j = 0; j < nt; ++j) {
     if (tid < NB) bj[tid] = __ldcg(b + (long)j * NB + tid);  // written by other CTAs in the previous step: bypass L1
@@ -135,16 +135,26 @@ __global__ void __launch_bounds__(256) trsv_fwd_coop_kernel(const double* __rest
     if (h == 0) xj[r] = s + part[r];
     __syncthreads();
     if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
+    // rows below: 64 rows per CTA pass, 4 threads per row (one quarter of the 128 columns each) for memory-level
+    // parallelism; the quarters are combined in shared memory in a fixed order
     const long first = (long)(j + 1) * NB;
-    for (long row = first + (long)blockIdx.x * 256 + tid; row < n; row += (long)gridDim.x * 256) {
-      const double* Lp = L + row + (long)j * NB * ld;
+    const int rr = tid & 63, cq = tid >> 6;
+    for (long row0 = first + (long)blockIdx.x * 64; row0 < n; row0 += (long)gridDim.x * 64) {
+      const long row = row0 + rr;
       double acc = 0.0, acc2 = 0.0;
+      if (row < n) {
+        const double* Lp = L + row + ((long)j * NB + cq * 32) * ld;
+        const double* xq = xj + cq * 32;
 #pragma unroll 16
-      for (int c = 0; c < NB; c += 2) {
-        acc = fma(Lp[(long)c * ld], xj[c], acc);
-        acc2 = fma(Lp[(long)(c + 1) * ld], xj[c + 1], acc2);
+        for (int c = 0; c < 32; c += 2) {
+          acc = fma(Lp[(long)c * ld], xq[c], acc);
+          acc2 = fma(Lp[(long)(c + 1) * ld], xq[c + 1], acc2);
+        }
       }
-      b[row] = __ldcg(b + row) - (acc + acc2);
+      quart[cq * 64 + rr] = acc + acc2;
+      __syncthreads();
+      if (tid < 64 && row < n) b[row] = __ldcg(b + row) - ((quart[rr] + quart[64 + rr]) + (quart[128 + rr] + quart[192 + rr]));
+      __syncthreads();
     }
     grid.sync();
   }
@@ -214,7 +224,7 @@ inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const doub
   int nt = (int)(n / NB);
   GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   {
-    const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 255) / 256);
+    const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 63) / 64);
     void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&n, (void*)&work, (void*)&tmp};
     GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_fwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
     ctx->launches++;
@@ -232,7 +242,7 @@ inline int trsv_forward(gprc_ctx* ctx, const double* L, long n, long ld, const d
                         double* work, double* x) {
   int nt = (int)(n / NB);
   GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 255) / 256);
+  const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 63) / 64);
   void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&n, (void*)&work, (void*)&x};
   GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_fwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
   ctx->launches++;
