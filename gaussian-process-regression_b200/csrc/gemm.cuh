@@ -170,12 +170,15 @@ __device__ __forceinline__ void tri_decode(long t, int& i, int& j) {
 // SYRK / panel update on lower tiles:  C(ti, tj) -= sum_{k in [k0, k1)} P(ti, k) P(tj, k)^T
 //   mode 0 (column): tj = col_tile, ti = col_tile + blockIdx.x
 //   mode 1 (trail):  (ti, tj) enumerate the lower triangle of tiles [first_tile, ntiles)
+//   mode 2 (strips): the block columns tj in [first_tile, first_tile + ncols), each with its row tiles ti in [tj, nt)
+//                    (the lookahead update of a whole outer panel in one launch)
 // ---------------------------------------------------------------------------------------------------------------
 struct SyrkPolicy {
   static constexpr bool B_KMAJOR = false;
   double* A;
   long ld;
   int mode, first_tile, k0, k1;
+  int ncols = 1, nt = 0;  // mode 2 only
   struct Tile {
     double* C;
   };
@@ -184,6 +187,16 @@ struct SyrkPolicy {
     if (mode == 0) {
       tj = first_tile;
       ti = first_tile + blockIdx.x;
+    } else if (mode == 2) {
+      int idx = blockIdx.x;
+      tj = first_tile;
+      for (int q = 0; q < ncols; ++q, ++tj) {
+        const int cnt = nt - tj;
+        if (idx < cnt) break;
+        idx -= cnt;
+      }
+      if (tj >= first_tile + ncols) return false;
+      ti = tj + idx;
     } else {
       tri_decode(blockIdx.x, ti, tj);
       ti += first_tile;

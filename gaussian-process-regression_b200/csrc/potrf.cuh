@@ -231,9 +231,11 @@ inline int potrf_blocked(gprc_ctx* ctx, double* A, long n, long ld, double* dinv
     const int Nend = (Jend + OB < nt) ? Jend + OB : nt;
     // LA(P): columns of the next panel, on the panel stream, after rest(P - 1) has finished with them
     if (J0 > 0) GPRC_CUDA(cudaStreamWaitEvent(s1, ctx->ev_rest, 0));
-    for (int tj = Jend; tj < Nend; ++tj) {
-      SyrkPolicy p{A, ld, 0, tj, J0 * NB, Jend * NB};
-      GPRC_CHECK(launch_gemm(ctx, p, dim3(nt - tj), s1));
+    {
+      long tiles = 0;
+      for (int tj = Jend; tj < Nend; ++tj) tiles += nt - tj;
+      SyrkPolicy p{A, ld, 2, Jend, J0 * NB, Jend * NB, Nend - Jend, nt};
+      GPRC_CHECK(launch_gemm(ctx, p, dim3((unsigned)tiles), s1));
     }
     // rest(P): everything right of the next panel, on the main stream, once panel P is factored
     GPRC_CUDA(cudaStreamWaitEvent(s0, ctx->ev_panel, 0));
