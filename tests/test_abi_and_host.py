@@ -199,3 +199,29 @@ def test_bench_test_point_shards_cover_exactly():
         cuts = [(r * m // world, (r + 1) * m // world) for r in range(world)]
         assert cuts[0][0] == 0 and cuts[-1][1] == m
         assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def _build_c_client(tmp_path):
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_abi_smoke.c"),
+                    "-L" + PKG, "-lgprc", "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_plain_c_client_links_against_the_abi(tmp_path):
+    """include/gprc.h is a C header and libgprc.so links into a C program with no C++/Python/R in sight; without a GPU
+    the client reports the loud failure of gprc_ctx_create."""
+    exe = _build_c_client(tmp_path)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the gpu test")
+    r = subprocess.run([exe], env=dict(os.environ, LD_LIBRARY_PATH=PKG), capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_reproduces_known_answers(tmp_path):
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], env=dict(os.environ, LD_LIBRARY_PATH=PKG), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "all known answers reproduced through the C ABI" in r.stdout
