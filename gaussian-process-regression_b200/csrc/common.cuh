@@ -53,11 +53,6 @@ inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
 }  // namespace gprc
 
 struct gprc_ctx {

@@ -122,21 +122,6 @@ __global__ void fill_kernel(double* p, long n, double v) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
-// dst (ldd) <- src (lds) for an r x c block, rest of the rp x cp padded block: 0, or 1 on the diagonal
-__global__ void pad_copy_kernel(const double* __restrict__ src, long lds, long r, long c, double* __restrict__ dst,
-                                long ldd, long rp, long cp, int pad_identity, double diag_add) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long j = blockIdx.y;
-  if (i >= rp || j >= cp) return;
-  double v;
-  if (i < r && j < c) {
-    v = src[i + j * lds];
-    if (i == j) v += diag_add;
-  } else {
-    v = (pad_identity && i == j) ? 1.0 : 0.0;
-  }
-  dst[i + j * ldd] = v;
-}
 // tmp[i + jj n] = (i >= j0 + jj) ? M[i + (j0 + jj) ld] : 0   (download of a lower-triangular factor, explicit zeros)
 __global__ void tril_slab_kernel(const double* __restrict__ M, long ld, long n, long j0, long nc,
                                  double* __restrict__ tmp) {

@@ -11,7 +11,8 @@ namespace gprc {
 
 constexpr int TRSV_ROWS = 512;  // rows of the rank-128 update per CTA
 
-// One block step of the forward substitution L x = b:
+// One block step of the forward substitution L x = b (used by the multi-GPU solve, where a rank only owns some
+// block columns; the single-GPU solve uses the cooperative sweeps below):
 //   x_j = Linv_j b_j   (every CTA, redundantly; CTA 0 stores it)
 //   b[rows below] -= L[rows, block j] x_j
 // b is the working right-hand side (blocks > j are updated in place), x receives the solution.
@@ -49,61 +50,6 @@ __global__ void __launch_bounds__(256) trsv_fwd_step_kernel(const double* __rest
       }
       b[row] -= acc + acc2;
     }
-  }
-}
-
-// One block step of the backward substitution L^T x = b (j runs from the last block to the first):
-//   x_j = Linv_j^T b_j ;  b[k] -= sum_c L[j*128 + c, k] x_j[c]  for k < j*128
-// warp per column so that the 128 contiguous rows of a column of L are read coalesced.
-__global__ void __launch_bounds__(256) trsv_bwd_step_kernel(const double* __restrict__ L, long ld,
-                                                            const double* __restrict__ dinv, int j,
-                                                            double* __restrict__ b, double* __restrict__ x) {
-  __shared__ double bj[NB], xj[NB];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < NB) bj[tid] = b[(long)j * NB + tid];
-  __syncthreads();
-  const double* Li = dinv + (long)j * NB * NB;
-  {
-    // x_j[r] = sum_{c >= r} Linv[c, r] b_j[c]: each warp owns 16 rows; all 64 loads of a lane are independent
-    double s[16];
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = warp + 8 * rr;
-      double acc = 0.0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = lane + 32 * q;
-        acc = fma(Li[c + r * NB], bj[c], acc);
-      }
-      s[rr] = acc;
-    }
-#pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
-      const double t = warp_sum(s[rr]);
-      if (lane == 0) xj[warp + 8 * rr] = t;
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && tid < NB) x[(long)j * NB + tid] = xj[tid];
-  if ((int)blockIdx.x >= j) return;         // j == 0: nothing left to update
-  const long col0 = (long)blockIdx.x * NB;  // this CTA updates columns [col0, col0 + 128), all < j * 128
-  const double* Lrow = L + (long)j * NB;
-  double xr[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) xr[q] = xj[lane + 32 * q];
-  double s[16];
-#pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    const double* Lp = Lrow + (col0 + warp + 8 * kk) * ld;
-    double acc = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc = fma(Lp[lane + 32 * q], xr[q], acc);
-    s[kk] = acc;
-  }
-#pragma unroll
-  for (int kk = 0; kk < 16; ++kk) {
-    const double t = warp_sum(s[kk]);
-    if (lane == 0) b[col0 + warp + 8 * kk] -= t;
   }
 }
 
@@ -237,18 +183,6 @@ inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const doub
   }
   return 0;
 }
-// only the forward half: x = L^-1 rhs
-inline int trsv_forward(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
-                        double* work, double* x) {
-  int nt = (int)(n / NB);
-  GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 63) / 64);
-  void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&n, (void*)&work, (void*)&x};
-  GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_fwd_coop_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
-  ctx->launches++;
-  return 0;
-}
-
 // y = K^T v for a column-major n x n matrix (K symmetric in the callers): warp per column, coalesced.
 __global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ K, long ld, long n,
                                                      const double* __restrict__ v, double* __restrict__ y) {
