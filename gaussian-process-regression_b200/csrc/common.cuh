@@ -59,12 +59,10 @@ struct gprc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_hi = nullptr;  // high priority: the latency-bound panel factorisation (Cholesky lookahead)
-  cudaStream_t stream_aux = nullptr; // second chunk pipeline of large predicts (fills the tail of partial waves)
-  cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr;
   int sm_count = 148;
   int opt_gram_dmma = 1;
   int opt_predict_path = 0;
-  int opt_dual_pipeline = 0;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};
   // pending (start, stop, phase) events; resolved lazily in gprc_ctx_get_timers so that timing never adds a sync

@@ -233,7 +233,7 @@ struct gprc_gpr {
   double* y = nullptr;  // n_pad
   double* alpha = nullptr;
   FactorState F;
-  PredictWorkspace ws, ws_b;  // ws_b: second chunk pipeline of large predicts
+  PredictWorkspace ws;
   double noise = 0, logp = 0;
 };
 
@@ -249,7 +249,7 @@ struct gprc_gpc {
   double* sw = nullptr;     // n_pad  sqrt(W) at f_hat
   double* gradl = nullptr;  // n_pad  (y + 1)/2 - P at f_hat
   FactorState F;            // factor of B = I + W^1/2 K W^1/2
-  PredictWorkspace ws, ws_b;
+  PredictWorkspace ws;
 };
 
 // =================================================================================================================
@@ -280,9 +280,6 @@ extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
   GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
   GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
-  GPRC_CUDA(cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo));
-  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
   GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
@@ -310,10 +307,6 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
   cudaFreeHost(c->h_scalars);
   cudaFreeHost(c->h_info);
   cudaStreamSynchronize(c->stream_hi);
-  cudaStreamSynchronize(c->stream_aux);
-  cudaEventDestroy(c->ev_fork);
-  cudaEventDestroy(c->ev_join);
-  cudaStreamDestroy(c->stream_aux);
   cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev_panel);
   cudaEventDestroy(c->ev_rest);
@@ -326,10 +319,6 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
   GPRC_ARG(c != nullptr);
   if (option == GPRC_OPT_GRAM_DMMA) {
     c->opt_gram_dmma = value;
-    return 0;
-  }
-  if (option == GPRC_OPT_DUAL_PIPELINE) {
-    c->opt_dual_pipeline = value ? 1 : 0;
     return 0;
   }
   if (option == GPRC_OPT_PREDICT_PATH) {
@@ -635,62 +624,47 @@ static int variance_pass_trsm(gprc_ctx* c, FactorState& F, PredictWorkspace& ws,
 }
 
 // mean/var for m test points (device pointers).  weights: alpha (GPR) or (y+1)/2 - P (GPC); rowscale: sqrt(W) or null.
+// one chunk of test points on the CURRENT c->stream with workspace w: K_star^T (+ mean partials), variance pass, finalize
+static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F, PredictWorkspace& w,
+                         const double* weights, const double* rowscale, const double* dXs, long c0, long mcur,
+                         bool use_trsm, double* dmean, double* dvar) {
+  const long mpad = round_up(mcur, NB);
+  int mean_tile = CT;  // training points per partial of the mean: 64 (direct build) or 128 (tensor-core build)
+  {
+    PhaseTimer t(c, GPRC_T_BUILD_KS);
+    // K_star^T tile by tile: rows = test points, columns = training points; sqrt(W) scaling and the mean's weighted
+    // sums run along the training axis
+    GPRC_CHECK(cov_build_dev(c, k, dXs + c0 * d, d, mcur, dX, F.n, w.Ks, w.mc, mpad, F.n_pad, false, false, 0.0, false,
+                             nullptr, nullptr, w.pmean, w.mc, rowscale, weights, &mean_tile));
+    cov_pointwise_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(k, dXs + c0 * d, dXs + c0 * d, d, mcur,
+                                                                               w.kss);
+    c->launches++;
+  }
+  GPRC_CHECK(use_trsm ? variance_pass_trsm(c, F, w, mpad) : variance_pass(c, F, w, mpad, nullptr, 0));
+  finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
+      w.pmean, w.mc, (int)(F.n_pad / mean_tile), w.pvar, w.mc, (int)(F.n_pad / NB), w.kss, mcur, dmean + c0, dvar + c0);
+  c->launches++;
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F,
                                  PredictWorkspace& ws, const double* weights, const double* rowscale,
-                                 const double* dXs, long m, double* dmean, double* dvar,
-                                 PredictWorkspace* ws_b = nullptr) {
+                                 const double* dXs, long m, double* dmean, double* dvar) {
   // path of the variance pass: with W = L^-1 (one launch per chunk) or by blocked substitution (no inversion)
   const bool use_trsm = (c->opt_predict_path == 2) || (c->opt_predict_path == 0 && !F.W && m >= WAVE_COLS);
   if (!use_trsm) GPRC_CHECK(ensure_inverse(c, F));
-  GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
-  // Substitution path with several chunks: every launch is one wave of <= 148 CTAs, so a last chunk of r < 148 tiles
-  // leaves 148 - r SMs idle for a whole sweep.  GPRC_OPT_DUAL_PIPELINE = 1 alternates the chunks between two
-  // independent pipelines (two streams, two workspaces) so that the neighbouring chunk can fill the partial wave.
-  // Measured on B200 (n = 50k, 125 000 test points = 6.6 waves): 9.29 s against 9.42 s -- the block scheduler runs
-  // full-wave grids of the two streams one after the other rather than side by side, so most of the tail stays; the
-  // option is therefore OFF by default (a persistent per-tile scheduler is the real fix).
-  const bool dual = c->opt_dual_pipeline && use_trsm && ws_b && m > ws.mc;
-  if (dual) {
-    GPRC_CHECK(workspace_ensure(c, *ws_b, F.n_pad, m - ws.mc));
-    GPRC_CUDA(cudaEventRecord(c->ev_fork, c->stream));
-    GPRC_CUDA(cudaStreamWaitEvent(c->stream_aux, c->ev_fork, 0));
-  }
   PhaseTimer span(c, GPRC_T_PREDICT);
-  int mean_tile = CT;  // columns (training points) per partial of the mean: 64 (direct build) or 128 (tensor-core build)
-  int rc = 0, chunk = 0;
-  for (long c0 = 0; c0 < m && rc == 0; ++chunk) {
-    const bool on_aux = dual && (chunk & 1);
-    PredictWorkspace& w = on_aux ? *ws_b : ws;
-    if (on_aux) std::swap(c->stream, c->stream_aux);  // every helper below enqueues on c->stream
-    const long mcur = std::min(w.mc, m - c0);
-    const long mpad = round_up(mcur, NB);
-    do {
-      {
-        PhaseTimer t(c, GPRC_T_BUILD_KS);
-        // K_star^T tile by tile: rows = test points, columns = training points; sqrt(W) scaling and the mean's
-        // weighted sums run along the training axis
-        if ((rc = cov_build_dev(c, k, dXs + c0 * d, d, mcur, dX, F.n, w.Ks, w.mc, mpad, F.n_pad, false, false, 0.0,
-                                false, nullptr, nullptr, w.pmean, w.mc, rowscale, weights, &mean_tile)))
-          break;
-        cov_pointwise_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(k, dXs + c0 * d, dXs + c0 * d, d,
-                                                                                   mcur, w.kss);
-        c->launches++;
-      }
-      if ((rc = use_trsm ? variance_pass_trsm(c, F, w, mpad) : variance_pass(c, F, w, mpad, nullptr, 0))) break;
-      finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
-          w.pmean, w.mc, (int)(F.n_pad / mean_tile), w.pvar, w.mc, (int)(F.n_pad / NB), w.kss, mcur, dmean + c0,
-          dvar + c0);
-      c->launches++;
-      if (cudaGetLastError() != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, "launch failed in predict");
-    } while (0);
-    if (on_aux) std::swap(c->stream, c->stream_aux);
-    c0 += mcur;
-  }
-  if (dual) {
-    cudaEventRecord(c->ev_join, c->stream_aux);
-    cudaStreamWaitEvent(c->stream, c->ev_join, 0);
-  }
-  return rc;
+  // NB every launch of a substitution-path chunk is one grid of <= 148 CTAs that depends on the previous one, so a
+  // last chunk of r < 148 tiles leaves 148 - r SMs idle for a whole sweep (a shard of 125 000 points = 6.6 waves: 6 %).
+  // Running several chunk pipelines on concurrent streams was measured and does NOT recover it (2 pipelines 33.45 vs
+  // 33.40 TFLOP/s, 4 sub-wave pipelines 32.4, 8: 31.4 -- the block scheduler does not pack the grids); the fix is a
+  // persistent per-tile scheduler inside one kernel.
+  GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
+  for (long c0 = 0; c0 < m; c0 += ws.mc)
+    GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(ws.mc, m - c0), use_trsm, dmean,
+                             dvar));
+  return 0;
 }
 
 // same with K_star (n x m) and kss (m) given on the host (closure kernels)
@@ -783,7 +757,6 @@ static void gpr_destroy(gprc_gpr* g) {
   dfree(g->alpha);
   g->F.release();
   g->ws.release();
-  g->ws_b.release();
   delete g;
 }
 
@@ -886,8 +859,7 @@ extern "C" int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, doub
   GPRC_ARG(!g->precomputed);
   if (m == 0) return 0;
   DeviceGuard guard(g->ctx);
-  return predict_pointwise_dev(g->ctx, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar,
-                               &g->ws_b);
+  return predict_pointwise_dev(g->ctx, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar);
 }
 
 extern "C" int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* mean, double* var) {
@@ -903,8 +875,7 @@ extern "C" int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* m
     if ((rc = dmalloc(&dmean, (size_t)m))) break;
     if ((rc = dmalloc(&dvar, (size_t)m))) break;
     cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
-    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar,
-                                    &g->ws_b)))
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar)))
       break;
     cudaMemcpyAsync(mean, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
     cudaMemcpyAsync(var, dvar, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
@@ -1260,7 +1231,6 @@ static void gpc_destroy(gprc_gpc* g) {
   dfree(g->gradl);
   g->F.release();
   g->ws.release();
-  g->ws_b.release();
   delete g;
 }
 
@@ -1429,8 +1399,7 @@ extern "C" int gprc_gpc_predict_latent(gprc_gpc* g, const double* Xs, long m, do
     if ((rc = dmalloc(&dmean, (size_t)m))) break;
     if ((rc = dmalloc(&dvar, (size_t)m))) break;
     cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
-    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar,
-                                    &g->ws_b)))
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar)))
       break;
     cudaMemcpyAsync(fs_bar, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
     cudaMemcpyAsync(Vfs, dvar, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
@@ -1513,8 +1482,7 @@ extern "C" int gprc_gpc_predict_class(gprc_gpc* g, const double* Xs, long m, dou
         (rc = dmalloc(&dout, (size_t)m)) || (rc = dmalloc(&dier, (size_t)m)))
       break;
     cudaMemcpyAsync(dXs, Xs, sizeof(double) * g->d * m, cudaMemcpyHostToDevice, c->stream);
-    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar,
-                                    &g->ws_b)))
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->gradl, g->sw, dXs, m, dmean, dvar)))
       break;
     // dnorm(z, mean = fs_bar[i], sd = Vfs[i]): the latent VARIANCE is passed as sd, as the reference does (A.1)
     if ((rc = quad_dev(c, dmean, dvar, m, dout, dier))) break;

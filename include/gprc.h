@@ -56,9 +56,7 @@ enum {
   GPRC_OPT_PREDICT_PATH = 2 /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
                                (one launch per chunk; best for repeated / small predicts), 2 blocked substitution
                                (no n^3/3 inversion; chosen automatically for >= 18 944 test points) */
-  ,
-  GPRC_OPT_DUAL_PIPELINE = 3 /* 1: large substitution-path predicts alternate their chunks between two streams to
-                                fill the last partial wave; default 0 (measured gain 1.4 % only, see gprc.cu) */
+
 };
 
 /* what to fetch with gprc_gpr_get / gprc_gpc_get */
@@ -85,9 +83,7 @@ enum {
   GPRC_T_BUILD_KS = 4,  /* K_star tiles + mean                      */
   GPRC_T_VAR = 5,       /* v = L^-1 K_star with fused column norms  */
   GPRC_T_NEWTON = 6,    /* GPC Newton loop                          */
-  GPRC_T_PREDICT = 7,   /* whole predict call (K_star build + variance pass + finalize) as ONE span on the main
-                           stream; large predicts run two chunk pipelines concurrently, so the per-phase timers 4 and 5
-                           overlap in time there and this span is the wall-clock figure */
+  GPRC_T_PREDICT = 7,   /* whole predict call (K_star build + variance pass + finalize) as one span */
   GPRC_T_COUNT = 8
 };
 

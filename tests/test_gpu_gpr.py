@@ -184,22 +184,6 @@ def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
     assert_mean_var(got, ref, ok(Xs, Xs))
 
 
-def test_dual_pipeline_option_gives_identical_results(gprc, ctx):
-    rng = np.random.default_rng(33)
-    n, m = 200, 2 * 148 * 128 + 500
-    X = rng.uniform(-3, 3, (2, n))
-    y = np.sin(X[0]) * X[1] + rng.normal(0, 0.1, n)
-    Xs = rng.uniform(-3, 3, (2, m))
-    g = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
-    a = g.predict(Xs)
-    ctx.set_option(gprc._lib.OPT_DUAL_PIPELINE, 1)
-    try:
-        b = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx).predict(Xs)
-    finally:
-        ctx.set_option(gprc._lib.OPT_DUAL_PIPELINE, 0)
-    np.testing.assert_array_equal(a, b)
-
-
 def test_large_predict_takes_the_substitution_path(gprc, oracle, ctx):
     # >= 148 * 128 test points and no inverse yet: automatic choice = blocked substitution, whole-wave chunks
     rng = np.random.default_rng(32)

@@ -85,4 +85,4 @@ if "gpr" in what:
     print("gpr n=%d m=%d: fit %.3f s predict %.3f s launches %d timers %s" % (n, m, t1 - t0, t2 - t1, launches,
                                                                            {k: round(v, 2) for k, v in tm.items()}))
     print("  chol %.2f TF/s  trtri %.2f TF/s  var %.2f TF/s" % (n ** 3 / 3 / tm["chol"] / 1e9, (n ** 3 / 3 / tm["trtri"] / 1e9) if tm["trtri"] else float("nan"),
-                                                                 n * n * m / (tm.get("predict") or tm["var"]) / 1e9))
+                                                                 n * n * m / tm["var"] / 1e9))
