@@ -558,6 +558,155 @@ struct TrsmLeftDiagPolicy {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same substitution as ONE persistent kernel.  Work item = (block row i, tile t): update then diagonal solve,
+// handed out row by row by an atomic counter.  A block row of a tile only waits for the previous block row of the
+// SAME tile (tile columns never depend on each other): a per-tile progress counter in global
+// memory (release / acquire) replaces the grid-wide barrier that a kernel boundary is, so the items of neighbouring
+// block rows overlap and no SM idles when the number of tiles is not a multiple of 148.  Items are only ever assigned
+// to running CTAs and every prerequisite has a smaller index, so the scheme needs no co-residency guarantee.
+// Data written by other CTAs with ordinary stores is read here through the TMA engine: the acquiring CTA issues
+// fence.proxy.async before its bulk copies.
+// ---------------------------------------------------------------------------------------------------------------
+struct TrsmPersistParams {
+  const double* L;
+  long ldl;
+  const double* dinv;
+  double* T;
+  long ldt;
+  double* partial;
+  long ldp;
+  int nt, ntc;
+  unsigned long long* next;  // work counter (zeroed by the host)
+  int* progress;             // [ntc] items completed per tile (zeroed by the host)
+  int* error;                // watchdog: set if a dependency never arrives
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_persistent_kernel(const TrsmPersistParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + STAGES;
+  __shared__ long long s_item;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), GEMM_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // item = (block row i, tile t), row-major; it runs the update and then the diagonal solve of that block row for
+  // that tile.  Its only prerequisite, item (i - 1, t), was handed out ntc items earlier, so with ntc >= ~2 x 148 a
+  // fetched item is practically always ready and nobody spins.
+  const long long total = (long long)p.ntc * p.nt;
+  long long base = 0;  // k-slices this CTA has pushed through the ring so far (identical for producer and consumers)
+  const WarpCoord wc;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      long long item = (long long)atomicAdd(p.next, 1ULL);
+      if (item < total) {
+        const int t = (int)(item % p.ntc), i = (int)(item / p.ntc);
+        long long spins = 0;
+        while (ld_acquire_gpu(p.progress + t) < i) {
+          __nanosleep(200);
+          if (++spins > (1LL << 26)) {  // ~10 s: something is wrong; fail loudly instead of hanging the device
+            atomicExch(p.error, 1);
+            item = total;
+            break;
+          }
+        }
+        if (item < total && *reinterpret_cast<volatile int*>(p.error)) item = total;
+      }
+      s_item = item;
+    }
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= total) break;
+    const int t = (int)(item % p.ntc), i = (int)(item / p.ntc);
+    double* Ctile = p.T + (long)t * NB + (long)i * NB * p.ldt;  // element (m, n) of the tile at C[n + m * ldt]
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      // rows of T written with ordinary stores (by other CTAs before the acquire above, by this CTA in phase 0) are
+      // about to be read by the TMA engine
+      fence_proxy_async();
+      TileWork w;
+      if (phase == 0) {  // R_i = Ks_i - L[i, <i] V[<i]
+        w.A = p.L + (long)i * NB;
+        w.lda = p.ldl;
+        w.B = p.T + (long)t * NB;
+        w.ldb = p.ldt;
+        w.k_begin = 0;
+        w.k_end = i * NB;
+      } else {  // V_i = Linv_i R_i
+        w.A = p.dinv + (long)i * NB * NB;
+        w.lda = NB;
+        w.B = Ctile;
+        w.ldb = p.ldt;
+        w.k_begin = 0;
+        w.k_end = NB;
+      }
+      const int KT = (w.k_end - w.k_begin) / BK;
+      if (warp == GEMM_CONSUMERS / 32) {
+        if (lane == 0) {
+          for (int kt = 0; kt < KT; ++kt) {
+            const long long gk = base + kt;
+            const int s = (int)(gk % STAGES);
+            if (gk >= STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)(((gk / STAGES) - 1) & 1));
+            produce_stage<false>(w, w.k_begin + kt * BK, smem + s * STAGE_DOUBLES, smem_u32(full + s));
+          }
+        }
+      } else if (KT > 0) {
+        Acc acc;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+        if (phase == 0) {
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            int line = threadIdx.x + qq * GEMM_CONSUMERS;
+            prefetch_l2(Ctile + (long)(line >> 3) * p.ldt + (line & 7) * 16);
+          }
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+          const long long gk = base + kt;
+          const int s = (int)(gk % STAGES);
+          mbar_wait(smem_u32(full + s), (uint32_t)((gk / STAGES) & 1));
+          compute_stage<false>(smem + s * STAGE_DOUBLES, wc, acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(empty + s));
+        }
+        if (phase == 0) {
+          TrsmLeftUpdatePolicy pol{p.L, p.ldl, p.T, p.ldt, i};
+          TrsmLeftUpdatePolicy::Tile tile{Ctile};
+          pol.epilogue(tile, acc, smem);
+        } else {
+          TrsmLeftDiagPolicy pol{p.dinv + (long)i * NB * NB, p.T, p.ldt, i, p.partial, p.ldp};
+          TrsmLeftDiagPolicy::Tile tile{Ctile, t};
+          pol.epilogue(tile, acc, smem);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      base += KT;
+    }
+    if (threadIdx.x == 0) st_release_gpu(p.progress + t, i + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Plain DGEMM (tests, roofline microbenchmark):  C = beta C + alpha A op(B)
 // ---------------------------------------------------------------------------------------------------------------
 template <bool KMAJOR>

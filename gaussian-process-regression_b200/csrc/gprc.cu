@@ -198,12 +198,15 @@ struct PredictWorkspace {
   double* pmean = nullptr;  // (n_pad / 64) x mc
   double* pvar = nullptr;   // (n_pad / 128) x mc
   double* kss = nullptr;    // mc
+  int* sched = nullptr;     // persistent substitution kernel: [0..1] work counter, [2] error flag, [4..] per-tile progress
   void release() {
     dfree(Ks);
     dfree(pmean);
     dfree(pvar);
     dfree(kss);
+    dfree(sched);
     Ks = pmean = pvar = kss = nullptr;
+    sched = nullptr;
     mc = 0;
   }
 };
@@ -322,7 +325,7 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     return 0;
   }
   if (option == GPRC_OPT_PREDICT_PATH) {
-    GPRC_ARG(value >= 0 && value <= 2);
+    GPRC_ARG(value >= 0 && value <= 3);
     c->opt_predict_path = value;
     return 0;
   }
@@ -567,13 +570,13 @@ static int ensure_inverse(gprc_ctx* c, FactorState& F) {
 
 constexpr long WAVE_COLS = 148L * NB;  // test points of one full wave of 128-wide tiles on 148 SMs
 
-static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m) {
+static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m, double max_bytes = 8.0e9) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   long want = round_up(std::max<long>(m, 1), NB);
   // per test point: Ks column + partial rows
   const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1);
-  const double budget = std::min(8.0e9, 0.45 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
+  const double budget = std::min(max_bytes, 0.45 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
   long cap = (long)(budget / per_col) / NB * NB;
   cap = std::max<long>(cap, NB);
   cap = std::min<long>(cap, 1L << 20);
@@ -585,6 +588,7 @@ static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long 
   GPRC_CHECK(dmalloc(&ws.pmean, (size_t)(n_pad / CT) * want));
   GPRC_CHECK(dmalloc(&ws.pvar, (size_t)(n_pad / NB) * want));
   GPRC_CHECK(dmalloc(&ws.kss, (size_t)want));
+  GPRC_CHECK(dmalloc(&ws.sched, (size_t)(want / NB + 8)));
   ws.mc = want;
   return 0;
 }
@@ -623,11 +627,42 @@ static int variance_pass_trsm(gprc_ctx* c, FactorState& F, PredictWorkspace& ws,
   return 0;
 }
 
+// ... and as ONE persistent kernel with per-tile progress counters (no launch boundary between block rows)
+static int variance_pass_persistent(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur_pad) {
+  static bool configured[64] = {false};
+  if (!configured[c->device & 63]) {
+    GPRC_CUDA(cudaFuncSetAttribute(trsm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    configured[c->device & 63] = true;
+  }
+  const int nt = (int)(F.n_pad / NB), ntc = (int)(mcur_pad / NB);
+  PhaseTimer t(c, GPRC_T_VAR);
+  GPRC_CUDA(cudaMemsetAsync(ws.sched, 0, sizeof(int) * (ntc + 8), c->stream));
+  TrsmPersistParams p;
+  p.L = F.L;
+  p.ldl = F.n_pad;
+  p.dinv = F.dinv;
+  p.T = ws.Ks;
+  p.ldt = ws.mc;
+  p.partial = ws.pvar;
+  p.ldp = ws.mc;
+  p.nt = nt;
+  p.ntc = ntc;
+  p.next = reinterpret_cast<unsigned long long*>(ws.sched);
+  p.error = ws.sched + 2;
+  p.progress = ws.sched + 4;
+  const int grid = std::min(c->sm_count, ntc);
+  trsm_persistent_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, c->stream>>>(p);
+  c->launches++;
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // mean/var for m test points (device pointers).  weights: alpha (GPR) or (y+1)/2 - P (GPC); rowscale: sqrt(W) or null.
 // one chunk of test points on the CURRENT c->stream with workspace w: K_star^T (+ mean partials), variance pass, finalize
 static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F, PredictWorkspace& w,
                          const double* weights, const double* rowscale, const double* dXs, long c0, long mcur,
-                         bool use_trsm, double* dmean, double* dvar) {
+                         int path /* 1 inverse, 2 substitution, 3 persistent substitution */, double* dmean,
+                         double* dvar) {
   const long mpad = round_up(mcur, NB);
   int mean_tile = CT;  // training points per partial of the mean: 64 (direct build) or 128 (tensor-core build)
   {
@@ -640,7 +675,9 @@ static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d
                                                                                w.kss);
     c->launches++;
   }
-  GPRC_CHECK(use_trsm ? variance_pass_trsm(c, F, w, mpad) : variance_pass(c, F, w, mpad, nullptr, 0));
+  GPRC_CHECK(path == 3   ? variance_pass_persistent(c, F, w, mpad)
+             : path == 2 ? variance_pass_trsm(c, F, w, mpad)
+                         : variance_pass(c, F, w, mpad, nullptr, 0));
   finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
       w.pmean, w.mc, (int)(F.n_pad / mean_tile), w.pvar, w.mc, (int)(F.n_pad / NB), w.kss, mcur, dmean + c0, dvar + c0);
   c->launches++;
@@ -651,19 +688,59 @@ static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d
 static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F,
                                  PredictWorkspace& ws, const double* weights, const double* rowscale,
                                  const double* dXs, long m, double* dmean, double* dvar) {
-  // path of the variance pass: with W = L^-1 (one launch per chunk) or by blocked substitution (no inversion)
-  const bool use_trsm = (c->opt_predict_path == 2) || (c->opt_predict_path == 0 && !F.W && m >= WAVE_COLS);
-  if (!use_trsm) GPRC_CHECK(ensure_inverse(c, F));
+  // path of the variance pass: 1 = with W = L^-1 (one triangular GEMM per chunk); 2 = blocked substitution, two
+  // launches per block row (whole-wave chunks); 3 = the same substitution as one persistent kernel per chunk.
+  // auto: large predicts without an inverse at hand take 3, everything else 1.
+  int path = c->opt_predict_path;
+  const bool planned = (path == 0 && !F.W && m >= WAVE_COLS);  // large predict, no inverse at hand: substitution
+  if (path == 0 && !planned) path = 1;
+  if (path == 1) GPRC_CHECK(ensure_inverse(c, F));
   PhaseTimer span(c, GPRC_T_PREDICT);
-  // NB every launch of a substitution-path chunk is one grid of <= 148 CTAs that depends on the previous one, so a
-  // last chunk of r < 148 tiles leaves 148 - r SMs idle for a whole sweep (a shard of 125 000 points = 6.6 waves: 6 %).
+  if (planned) {
+    // Mixed plan.  Whole waves of 148 tiles go through the multi-launch substitution (all CTAs sweep the same block row
+    // in lockstep: the L row panel is shared in L2, 35.4 TFLOP/s); the last wave is merged with the remainder into ONE
+    // chunk of 148 + r tiles for the persistent kernel, which packs them without idle SMs (33.9 TFLOP/s because its CTAs
+    // drift apart along k).  125 000 points = 6.6 waves: 5 waves + a 237-tile persistent chunk instead of 7 sweeps.
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 20.0e9));
+    const long tiles = (m + NB - 1) / NB, cap_tiles = ws.mc / NB, rem = tiles % 148;
+    long last_tiles = (rem == 0) ? 0 : ((tiles >= 148 && cap_tiles >= 148 + rem) ? 148 + rem : rem);
+    long c0 = 0;
+    for (long left = tiles - last_tiles; left > 0;) {
+      const long take = std::min(left, cap_tiles);
+      GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(take * NB, m - c0), 2, dmean, dvar));
+      c0 += take * NB;
+      left -= take;
+    }
+    if (last_tiles > 0) {
+      GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, m - c0, 3, dmean, dvar));
+      GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      GPRC_CUDA(cudaStreamSynchronize(c->stream));
+      if (*reinterpret_cast<int*>(c->h_info) != 0)
+        return set_error(-6, __FILE__, __LINE__, "persistent substitution kernel: a tile dependency never arrived");
+    }
+    return 0;
+  }
+  if (path == 3) {
+    // everything through the persistent kernel: big balanced chunks
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 40.0e9));
+    const long tiles = (m + NB - 1) / NB, cap_tiles = ws.mc / NB;
+    const long nchunks = (tiles + cap_tiles - 1) / cap_tiles;
+    const long per = ((tiles + nchunks - 1) / nchunks) * NB;
+    for (long c0 = 0; c0 < m; c0 += per)
+      GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(per, m - c0), 3, dmean, dvar));
+    GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GPRC_CUDA(cudaStreamSynchronize(c->stream));
+    if (*reinterpret_cast<int*>(c->h_info) != 0)
+      return set_error(-6, __FILE__, __LINE__, "persistent substitution kernel: a tile dependency never arrived");
+    return 0;
+  }
+  // NB every launch of a substitution-path chunk (path 2) is one grid of <= 148 CTAs that depends on the previous one,
+  // so a last chunk of r < 148 tiles leaves 148 - r SMs idle for a whole sweep (125 000 points = 6.6 waves: 6 %).
   // Running several chunk pipelines on concurrent streams was measured and does NOT recover it (2 pipelines 33.45 vs
-  // 33.40 TFLOP/s, 4 sub-wave pipelines 32.4, 8: 31.4 -- the block scheduler does not pack the grids); the fix is a
-  // persistent per-tile scheduler inside one kernel.
+  // 33.40 TFLOP/s, 4 sub-wave pipelines 32.4, 8: 31.4 -- the block scheduler does not pack the grids); path 3 does.
   GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
   for (long c0 = 0; c0 < m; c0 += ws.mc)
-    GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(ws.mc, m - c0), use_trsm, dmean,
-                             dvar));
+    GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(ws.mc, m - c0), path, dmean, dvar));
   return 0;
 }
 

@@ -54,8 +54,10 @@ enum {
                              them); 1 (default): where it measured faster (dot-product kernels, d >= 12); 2: wherever
                              eligible */
   GPRC_OPT_PREDICT_PATH = 2 /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
-                               (one launch per chunk; best for repeated / small predicts), 2 blocked substitution
-                               (no n^3/3 inversion; chosen automatically for >= 18 944 test points) */
+                               (one launch per chunk; best for repeated / small predicts), 2 blocked substitution with
+                               two launches per block row (no n^3/3 inversion), 3 the same substitution as one
+                               persistent kernel with per-tile progress counters (chosen automatically for >= 18 944
+                               test points when no inverse exists yet) */
 
 };
 

@@ -166,7 +166,7 @@ def test_large_size_properties(gprc):
     np.testing.assert_allclose(ptrain[:, 0], y[:256] - 0.01 * g.alpha[:256], rtol=0, atol=1e-8)
 
 
-@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("path", [1, 2, 3])
 def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
     """v = L^-1 K_star either with the explicit inverse (one triangular GEMM) or by blocked substitution."""
     rng = np.random.default_rng(31)
@@ -182,6 +182,22 @@ def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
     ok = oracle.cov_func(oracle.rationalquadratic, l=0.8, alpha=1.5)
     ref = oracle.GPR(X, y, 0.05, ok).predict(Xs)
     assert_mean_var(got, ref, ok(Xs, Xs))
+
+
+def test_persistent_and_multi_launch_substitution_are_bitwise_equal(gprc, ctx):
+    rng = np.random.default_rng(34)
+    n, m = 520, 148 * 128 + 300   # 151 tiles on 148 SMs: block rows of neighbouring tiles overlap in the persistent kernel
+    X = rng.uniform(-3, 3, (2, n))
+    y = np.sin(X[0]) * X[1] + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-3, 3, (2, m))
+    out = []
+    for path in (2, 3):
+        ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
+        try:
+            out.append(gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx).predict(Xs))
+        finally:
+            ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
+    np.testing.assert_array_equal(out[0], out[1])
 
 
 def test_large_predict_takes_the_substitution_path(gprc, oracle, ctx):
