@@ -22,6 +22,7 @@ GET_L, GET_ALPHA, GET_LINV, GET_FHAT, GET_SQRTW = range(5)
 GRAD_AS_CODED, GRAD_TEXTBOOK = 0, 1
 OPT_GRAM_DMMA = 1
 OPT_PREDICT_PATH = 2
+OPT_OZAKI_DIGITS = 3
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 
 

@@ -63,6 +63,7 @@ struct gprc_ctx {
   int sm_count = 148;
   int opt_gram_dmma = 1;
   int opt_predict_path = 0;
+  int opt_ozaki_digits = 7;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};
   // pending (start, stop, phase) events; resolved lazily in gprc_ctx_get_timers so that timing never adds a sync

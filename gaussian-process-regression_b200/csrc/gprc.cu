@@ -10,6 +10,7 @@
 #include "trsv.cuh"
 #include "gpc.cuh"
 #include "quad.cuh"
+#include "ozaki.cuh"
 
 namespace gprc {
 thread_local std::string g_last_error;
@@ -199,14 +200,26 @@ struct PredictWorkspace {
   double* pvar = nullptr;   // (n_pad / 128) x mc
   double* kss = nullptr;    // mc
   int* sched = nullptr;     // persistent substitution kernel: [0..1] work counter, [2] error flag, [4..] per-tile progress
+  // INT8 (Ozaki) substitution, ozaki.cuh: digit tiles of V, per-test-point exponent and scale; lazily allocated
+  int8_t* ozVs = nullptr;
+  int* oz_ecol = nullptr;
+  double* oz_scol = nullptr;
+  size_t oz_bytes = 0;
   void release() {
     dfree(Ks);
     dfree(pmean);
     dfree(pvar);
     dfree(kss);
     dfree(sched);
+    dfree(ozVs);
+    dfree(oz_ecol);
+    dfree(oz_scol);
     Ks = pmean = pvar = kss = nullptr;
     sched = nullptr;
+    ozVs = nullptr;
+    oz_ecol = nullptr;
+    oz_scol = nullptr;
+    oz_bytes = 0;
     mc = 0;
   }
 };
@@ -217,12 +230,24 @@ struct FactorState {  // a factored SPD matrix and everything derived from it
   double* dinv = nullptr;  // nt x 128 x 128 inverted diagonal blocks
   double* diag = nullptr;  // n_pad
   double* W = nullptr;     // lazy: L^-1, n_pad x n_pad lower
+  // lazy, INT8 (Ozaki) substitution: digit tiles of the strictly-lower block part of L, row exponents and scales
+  int8_t* ozLs = nullptr;
+  int* oz_erow = nullptr;
+  double* oz_srow = nullptr;
+  int oz_digits = 0;
   void release() {
     dfree(L);
     dfree(dinv);
     dfree(diag);
     dfree(W);
+    dfree(ozLs);
+    dfree(oz_erow);
+    dfree(oz_srow);
     L = dinv = diag = W = nullptr;
+    ozLs = nullptr;
+    oz_erow = nullptr;
+    oz_srow = nullptr;
+    oz_digits = 0;
   }
 };
 
@@ -325,8 +350,13 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     return 0;
   }
   if (option == GPRC_OPT_PREDICT_PATH) {
-    GPRC_ARG(value >= 0 && value <= 3);
+    GPRC_ARG(value >= 0 && value <= 4);
     c->opt_predict_path = value;
+    return 0;
+  }
+  if (option == GPRC_OPT_OZAKI_DIGITS) {
+    GPRC_ARG(value >= 6 && value <= 8);
+    c->opt_ozaki_digits = value;
     return 0;
   }
   return set_error(-1, __FILE__, __LINE__, "unknown option");
@@ -657,11 +687,91 @@ static int variance_pass_persistent(gprc_ctx* c, FactorState& F, PredictWorkspac
   return 0;
 }
 
+// ... and with the O(n^2 m) products on the INT8 tensor cores (ozaki.cuh): per block row one tcgen05 update launch,
+// the FP64 diagonal solve (same kernel as path 2) and the digit split of the new block row of V.
+// ws.sched[3] collects the overflow / watchdog flags; the caller checks it after the chunk.
+template <int S>
+static int oz_factor_digits(gprc_ctx* c, FactorState& F) {
+  const int nt = (int)(F.n_pad / NB);
+  if (!F.ozLs || F.oz_digits != S) {
+    dfree(F.ozLs);
+    F.ozLs = nullptr;
+    GPRC_CHECK(dmalloc(&F.ozLs, (size_t)F.n_pad * F.n_pad * S));
+    if (!F.oz_erow) GPRC_CHECK(dmalloc(&F.oz_erow, (size_t)F.n_pad));
+    if (!F.oz_srow) GPRC_CHECK(dmalloc(&F.oz_srow, (size_t)F.n_pad));
+    F.oz_digits = 0;
+  } else {
+    return 0;
+  }
+  int* flag = nullptr;
+  GPRC_CHECK(dmalloc(&flag, 1));
+  GPRC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  oz::rowmax_kernel<<<nt, 256, 0, c->stream>>>(F.L, F.n_pad, F.oz_erow, F.oz_srow);
+  oz::split_l_kernel<S><<<dim3(4 * nt, nt), 256, 0, c->stream>>>(F.L, F.n_pad, F.oz_erow, F.ozLs, (int)(F.n_pad / oz::BK), flag);
+  c->launches += 2;
+  GPRC_CUDA(cudaMemcpyAsync(c->h_info, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  dfree(flag);
+  if (*reinterpret_cast<int*>(c->h_info) != 0)
+    return set_error(-7, __FILE__, __LINE__, "INT8 substitution: L has non-finite entries");
+  F.oz_digits = S;
+  return 0;
+}
+
+template <int S>
+static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur, long mcur_pad) {
+  static bool configured[64] = {false};
+  if (!configured[c->device & 63]) {
+    GPRC_CUDA(cudaFuncSetAttribute(oz::update_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    configured[c->device & 63] = true;
+  }
+  GPRC_CHECK(oz_factor_digits<S>(c, F));
+  const size_t need = (size_t)ws.mc * F.n_pad * S;
+  if (ws.oz_bytes < need) {
+    dfree(ws.ozVs);
+    ws.ozVs = nullptr;
+    ws.oz_bytes = 0;
+    GPRC_CHECK(dmalloc(&ws.ozVs, need));
+    ws.oz_bytes = need;
+  }
+  if (!ws.oz_ecol) GPRC_CHECK(dmalloc(&ws.oz_ecol, (size_t)ws.mc));
+  if (!ws.oz_scol) GPRC_CHECK(dmalloc(&ws.oz_scol, (size_t)ws.mc));
+  const int nt = (int)(F.n_pad / NB), ntc = (int)(mcur_pad / NB), KB = (int)(F.n_pad / oz::BK);
+  int* flag = ws.sched + 3;
+  PhaseTimer t(c, GPRC_T_VAR);
+  GPRC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  oz::colscale_kernel<<<(unsigned)((mcur_pad + 255) / 256), 256, 0, c->stream>>>(ws.kss, mcur, mcur_pad, ws.oz_ecol, ws.oz_scol);
+  c->launches++;
+  for (int i = 0; i < nt; ++i) {
+    if (i > 0) {
+      oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 128u, 256u, 0};
+      oz::update_kernel<S><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
+      c->launches++;
+    }
+    TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};
+    GPRC_CHECK(launch_gemm(c, dg, dim3((unsigned)ntc)));
+    if (i + 1 < nt) {
+      oz::split_v_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN), 4), 128, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
+      c->launches++;
+    }
+  }
+  GPRC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int variance_pass_ozaki(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur, long mcur_pad) {
+  switch (c->opt_ozaki_digits) {
+    case 6: return variance_pass_ozaki_t<6>(c, F, ws, mcur, mcur_pad);
+    case 8: return variance_pass_ozaki_t<8>(c, F, ws, mcur, mcur_pad);
+    default: return variance_pass_ozaki_t<7>(c, F, ws, mcur, mcur_pad);
+  }
+}
+
 // mean/var for m test points (device pointers).  weights: alpha (GPR) or (y+1)/2 - P (GPC); rowscale: sqrt(W) or null.
 // one chunk of test points on the CURRENT c->stream with workspace w: K_star^T (+ mean partials), variance pass, finalize
 static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d, FactorState& F, PredictWorkspace& w,
                          const double* weights, const double* rowscale, const double* dXs, long c0, long mcur,
-                         int path /* 1 inverse, 2 substitution, 3 persistent substitution */, double* dmean,
+                         int path /* 1 inverse, 2 substitution, 3 persistent substitution, 4 INT8 substitution */, double* dmean,
                          double* dvar) {
   const long mpad = round_up(mcur, NB);
   int mean_tile = CT;  // training points per partial of the mean: 64 (direct build) or 128 (tensor-core build)
@@ -675,7 +785,8 @@ static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d
                                                                                w.kss);
     c->launches++;
   }
-  GPRC_CHECK(path == 3   ? variance_pass_persistent(c, F, w, mpad)
+  GPRC_CHECK(path == 4   ? variance_pass_ozaki(c, F, w, mcur, mpad)
+             : path == 3 ? variance_pass_persistent(c, F, w, mpad)
              : path == 2 ? variance_pass_trsm(c, F, w, mpad)
                          : variance_pass(c, F, w, mpad, nullptr, 0));
   finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
@@ -732,6 +843,21 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     GPRC_CUDA(cudaStreamSynchronize(c->stream));
     if (*reinterpret_cast<int*>(c->h_info) != 0)
       return set_error(-6, __FILE__, __LINE__, "persistent substitution kernel: a tile dependency never arrived");
+    return 0;
+  }
+  if (path == 4) {
+    // INT8 substitution: whole-wave chunks like path 2; the overflow / watchdog flag is read after every chunk and a
+    // flagged chunk (a K_star that violates |v| <= sqrt(k**), i.e. not a covariance of this model) is redone in FP64
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 12.0e9));
+    for (long c0 = 0; c0 < m; c0 += ws.mc) {
+      const long mcur = std::min(ws.mc, m - c0);
+      GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 4, dmean, dvar));
+      GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      GPRC_CUDA(cudaStreamSynchronize(c->stream));
+      const int flag = *reinterpret_cast<int*>(c->h_info);
+      if (flag & ~3) return set_error(-6, __FILE__, __LINE__, "INT8 substitution kernel: a pipeline barrier never completed");
+      if (flag) GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 2, dmean, dvar));
+    }
     return 0;
   }
   // NB every launch of a substitution-path chunk (path 2) is one grid of <= 148 CTAs that depends on the previous one,

@@ -1,0 +1,429 @@
+// ozaki.cuh -- the variance pass v = L^-1 K_star on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators).
+//
+// FP64 has no tcgen05 kind on sm_100a: the DMMA path (gemm.cuh) is pinned at 37 TFLOP/s, and the variance pass
+// (n^2 m flops, R/GPRclass.R:162-164) already runs at that ceiling.  The only way past it is to do the O(n^2 m)
+// product of the blocked substitution,  R_i = Ks_i - L[i, <i] V[<i],  in exact integer arithmetic on the 4.5 POP/s
+// INT8 pipe (Ozaki splitting) and keep FP64 for the O(n m 128) diagonal solves:
+//
+//   * every operand entry is written as a fixed-point number with S signed 8-bit digits,
+//       x = 2^(e - 8S + 2) * sum_t d_t 256^(S-1-t),   d_t in [-128, 127],   |x| < 2^e,
+//     e = per-row exponent for L (from the row maximum), per-test-point exponent for V (from |v| <= sqrt(k**),
+//     which holds because the predictive variance k** - v'v is non-negative);
+//   * digit products d_a d_b are exact in int32 and are accumulated over k by the tensor core; all pairs with the
+//     same order o = a + b share one TMEM accumulator (S accumulators of 128 x 64 int32 = S * 64 TMEM columns);
+//     pairs with a + b >= S are dropped (they sit below 2^(-8S+2) of the leading term);
+//   * every KC = 8192 k-values (int32 headroom: 7 pairs * 8192 * 2^14 < 2^31) the accumulators are drained:
+//       R -= 2^(eL-6) 2^(eV-6) sum_o acc_o 256^-o     (Horner in FP64, one rounding per term).
+//   S = 7 carries 54 bits below the row / column maximum: |var - var_fp64| ~ 1e-14 at n = 1024 (tools/oz_sim.py).
+//
+// Data layout: digits are stored pre-tiled in the canonical no-swizzle K-major UMMA layout, so that one k-step of one
+// tile (all S digit planes) is ONE contiguous block in global memory and one TMA bulk copy into shared memory:
+//   tile(rows R, 32 k):  byte offset of (r, k) = ((r / 8) * 2 + k / 16) * 128 + (r % 8) * 16 + k % 16
+//   (8 x 16 B core matrices; LBO = 128 B between the two k halves, SBO = 256 B between 8-row groups)
+//   Ls: [row block i][k block kb][digit s][128 x 32]      Vs: [64-point tile tc][k block kb][digit s][64 x 32]
+//
+// Kernel structure (one CTA per 128 L-rows x 64 test points, 192 threads):
+//   warp 0   producer: two bulk copies per k-step into a ring of shared-memory stages (full/empty mbarriers)
+//   warp 1   allocates TMEM; one lane issues S (S + 1) / 2 tcgen05.mma per k-step, tcgen05.commit releases the stage
+//   warps 2-5 drain TMEM (tcgen05.ld 32x32b), combine the orders, scale and update R in place.
+#pragma once
+#include "common.cuh"
+
+namespace gprc {
+namespace oz {
+
+constexpr int BM = 128;    // L rows per tile = one block row of the substitution
+constexpr int BN = 64;     // test points per tile
+constexpr int BK = 32;     // k per stage = K of one tcgen05.mma kind::i8
+constexpr int KC = 8192;   // drain interval (int32 headroom)
+constexpr int A_TILE = BM * BK;  // 4096 B
+constexpr int B_TILE = BN * BK;  // 2048 B
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+template <int S>
+struct Cfg {
+  static_assert(S >= 1 && S <= 8, "1..8 digits");
+  static constexpr int STAGE_BYTES = S * (A_TILE + B_TILE);
+  static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 8 ? 8 : (220 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+};
+
+__host__ __device__ __forceinline__ int tile_off(int r, int k) {
+  return ((r >> 3) * 2 + (k >> 4)) * 128 + (r & 7) * 16 + (k & 15);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// digits
+// ---------------------------------------------------------------------------------------------------------------
+// X = rint(x 2^((8S-2) - e)); balanced digits through the bias trick: Y = X + 0x80..80 (lower S-1 bytes), lower digit
+// t = byte_t(Y) - 128, top digit = Y >> 8(S-1).  sum_t digit_t 256^t = X exactly.
+template <int S>
+__host__ __device__ __forceinline__ long long to_fixed(double x, int e, bool* overflow) {
+  const double s = ldexp(x, -e);  // |s| < 1 nominally
+  if (!(fabs(s) < 1.9)) {
+    *overflow = true;
+    return 0;
+  }
+  return llrint(ldexp(s, 8 * S - 2));
+}
+template <int S>
+__host__ __device__ __forceinline__ long long biased(long long X) {
+  long long bias = 0;
+#pragma unroll
+  for (int t = 0; t < S - 1; ++t) bias |= 0x80LL << (8 * t);
+  return X + bias;
+}
+// digit plane s (0 = most significant) of a biased value
+template <int S>
+__host__ __device__ __forceinline__ int digit(long long Y, int s) {
+  const int t = S - 1 - s;
+  if (t == S - 1) return (int)(Y >> (8 * t));
+  return (int)((Y >> (8 * t)) & 0xFF) - 128;
+}
+
+// exponent e with |x| < 2^e (0 for x = 0)
+__host__ __device__ __forceinline__ int exponent_of(double mx) {
+  if (!(mx > 0.0)) return 0;
+  int e;
+  frexp(mx, &e);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// L: row maxima over the strictly-lower block part, exponents and scales
+// ---------------------------------------------------------------------------------------------------------------
+// grid = n_pad / 128 row blocks, 256 threads (row = tid % 128, two interleaved k phases)
+__global__ void __launch_bounds__(256) rowmax_kernel(const double* __restrict__ L, long ld, int* __restrict__ erow,
+                                                     double* __restrict__ scale_row) {
+  __shared__ double red[256];
+  const int i = blockIdx.x, r = threadIdx.x & 127, ph = threadIdx.x >> 7;
+  const double* p = L + (long)i * BM + r;
+  const long kend = (long)i * BM;
+  double mx = 0.0;
+  long k = ph;
+#pragma unroll 1
+  for (; k + 14 < kend; k += 16) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = fabs(p[(k + 2 * u) * ld]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) mx = fmax(mx, v[u]);
+  }
+  for (; k < kend; k += 2) mx = fmax(mx, fabs(p[k * ld]));
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  if (ph == 0) {
+    mx = fmax(red[r], red[r + 128]);
+    const int e = exponent_of(mx);
+    erow[(long)i * BM + r] = e;
+    scale_row[(long)i * BM + r] = ldexp(1.0, e - 6);
+  }
+}
+
+// grid (4 * nt, nt): blockIdx.y = row block i, blockIdx.x = k block kb (< 4 i); 256 threads = 128 rows x 2 k halves
+template <int S>
+__global__ void __launch_bounds__(256) split_l_kernel(const double* __restrict__ L, long ld, const int* __restrict__ erow,
+                                                      int8_t* __restrict__ Ls, int KB, int* __restrict__ error) {
+  const int i = blockIdx.y, kb = blockIdx.x;
+  if (kb >= 4 * i) return;
+  const int m = threadIdx.x & 127, kh = threadIdx.x >> 7;
+  const long row = (long)i * BM + m;
+  const int e = erow[row];
+  const double* p = L + row + ((long)kb * BK + kh * 16) * ld;
+  long long Y[16];
+  bool ovf = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) Y[j] = biased<S>(to_fixed<S>(p[(long)j * ld], e, &ovf));
+  if (ovf) atomicOr(error, 1);
+  int8_t* tile = Ls + ((long)i * KB + kb) * (long)(S * A_TILE) + tile_off(m, kh * 16);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v |= (uint32_t)(digit<S>(Y[q * 4 + b], s) & 0xFF) << (8 * b);
+      w[q] = v;
+    }
+    *reinterpret_cast<uint4*>(tile + s * A_TILE) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// V: per-test-point exponents from k**, digits of a freshly solved block row
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void colscale_kernel(const double* __restrict__ kss, long mcur, long mpad, int* __restrict__ ecol,
+                                double* __restrict__ scale_col) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= mpad) return;
+  int e = 0;
+  if (t < mcur) {
+    const double b = sqrt(fmax(kss[t], 0.0)) * (1.0 + 1e-9);
+    e = exponent_of(b);
+  }
+  ecol[t] = e;
+  scale_col[t] = ldexp(1.0, e - 6);
+}
+
+// block row i of V (rows k in [128 i, 128 i + 128), T[t + k ldt]) -> digit tiles.  grid (mpad / 64, 4), 128 threads
+template <int S>
+__global__ void __launch_bounds__(128) split_v_kernel(const double* __restrict__ T, long ldt, int i,
+                                                      const int* __restrict__ ecol, int8_t* __restrict__ Vs, int KB,
+                                                      int* __restrict__ error) {
+  const int tc = blockIdx.x, kq = blockIdx.y;
+  const int nn = threadIdx.x & 63, kh = threadIdx.x >> 6;
+  const long t = (long)tc * BN + nn;
+  const int e = ecol[t];
+  const double* p = T + t + ((long)i * BM + kq * BK + kh * 16) * ldt;
+  long long Y[16];
+  bool ovf = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) Y[j] = biased<S>(to_fixed<S>(p[(long)j * ldt], e, &ovf));
+  if (ovf) atomicOr(error, 2);
+  int8_t* tile = Vs + ((long)tc * KB + (4 * i + kq)) * (long)(S * B_TILE) + tile_off(nn, kh * 16);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v |= (uint32_t)(digit<S>(Y[q * 4 + b], s) & 0xFF) << (8 * b);
+      w[q] = v;
+    }
+    *reinterpret_cast<uint4*>(tile + s * B_TILE) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all tcgen05 operations issued so far by this thread have completed
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// this thread's TMEM lane, 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), LBO >> 4 at
+// [16,30), SBO >> 4 at [32,46), version 1 at [46,48), layout type 0 at [61,64))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 at [4,6)), A = B = signed 8 bit (1 at [7,10) and
+// [10,13)), both K-major (0 at 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t instr_desc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// try_wait with a watchdog: a dependency that never arrives raises the error flag and traps instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_guarded(uint32_t bar, uint32_t parity, int* error, int code) {
+  for (long spin = 0; !mbar_try(bar, parity); ++spin) {
+    if (spin > (1L << 24)) {  // try_wait itself blocks for a bounded time: 2^24 rounds are many seconds
+      atomicOr(error, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+struct UpdateParams {
+  const int8_t* Ls;         // digit tiles of L
+  const int8_t* Vs;         // digit tiles of V
+  const double* scale_row;  // 2^(eL - 6) per row of L
+  const double* scale_col;  // 2^(eV - 6) per test point
+  double* T;                // K_star^T, element (test point t, row k) at T[t + k ldt]
+  long ldt;
+  int i;   // block row
+  int KB;  // k blocks per row of tiles = n_pad / 32
+  int* error;
+  uint32_t lbo, sbo;  // descriptor strides (128 / 256 for the layout above)
+  int dbg;            // tools/oz_test only: 1 = no MMA (feed rate), 2 = no TMA (MMA rate), 4 = one bulk copy per digit
+};
+
+// R_i[128 x 64] -= L[i, <i] V[<i, tile]   one CTA per 64-test-point tile
+template <int S>
+__global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p) {
+  using C = Cfg<S>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tc = blockIdx.x;
+  const int KT = 4 * p.i;                      // k-steps
+  constexpr int KT_CHUNK = KC / BK;            // k-steps per drain
+  const int nchunks = (KT + KT_CHUNK - 1) / KT_CHUNK;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), 1);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    mbar_init(smem_u32(tmem_empty), 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      const int8_t* a_src = p.Ls + (long)p.i * p.KB * (long)(S * A_TILE);
+      const int8_t* b_src = p.Vs + (long)tc * p.KB * (long)(S * B_TILE);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % C::STAGES;
+        if (kt >= C::STAGES) mbar_wait_guarded(smem_u32(empty + s), ((kt / C::STAGES) - 1) & 1, p.error, 16);
+        const uint32_t bar = smem_u32(full + s);
+        const uint32_t dst = smem_u32(smem_raw + s * C::STAGE_BYTES);
+        if (p.dbg & 2) {
+          mbar_arrive(bar);
+          continue;
+        }
+        mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+        if (p.dbg & 4) {
+          for (int q = 0; q < S; ++q) {
+            bulk_g2s(dst + q * A_TILE, a_src + (long)kt * (S * A_TILE) + q * A_TILE, A_TILE, bar);
+            bulk_g2s(dst + S * A_TILE + q * B_TILE, b_src + (long)kt * (S * B_TILE) + q * B_TILE, B_TILE, bar);
+          }
+          continue;
+        }
+        bulk_g2s(dst, a_src + (long)kt * (S * A_TILE), S * A_TILE, bar);
+        bulk_g2s(dst + S * A_TILE, b_src + (long)kt * (S * B_TILE), S * B_TILE, bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_i8(BM, BN);
+      int kt = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        if (c > 0) {
+          mbar_wait_guarded(smem_u32(tmem_empty), (c - 1) & 1, p.error, 32);
+          tc_fence_after();
+        }
+        const int kt_end = min(KT, (c + 1) * KT_CHUNK);
+        for (bool first = true; kt < kt_end; ++kt, first = false) {
+          const int s = kt % C::STAGES;
+          mbar_wait_guarded(smem_u32(full + s), (kt / C::STAGES) & 1, p.error, 64);
+          tc_fence_after();
+          if (p.dbg & 1) {
+            mbar_arrive(smem_u32(empty + s));
+            continue;
+          }
+          const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES), b0 = a0 + S * A_TILE;
+#pragma unroll
+          for (int a = 0; a < S; ++a) {
+            const uint64_t ad = smem_desc(a0 + a * A_TILE, p.lbo, p.sbo);
+#pragma unroll
+            for (int b = 0; b < S - a; ++b) {
+              const uint64_t bd = smem_desc(b0 + b * B_TILE, p.lbo, p.sbo);
+              // the first product into accumulator a + b of this chunk is (0, a + b) at the chunk's first k-step
+              mma_i8(tmem_base + (uint32_t)((a + b) * BN), ad, bd, idesc, (!first || a > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(smem_u32(empty + s));  // stage s may be refilled once these MMAs have read it
+        }
+        tc_commit(smem_u32(tmem_full));  // accumulators of chunk c are complete
+      }
+    }
+  } else {
+    // ===== drain: TMEM -> registers -> R (in place) =====
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;       // row of the tile = TMEM lane
+    const double sr = p.scale_row[(long)p.i * BM + row];
+    double* crow = p.T + (long)tc * BN + ((long)p.i * BM + row) * p.ldt;
+    const double* sc = p.scale_col + (long)tc * BN;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait_guarded(smem_u32(tmem_full), c & 1, p.error, 128);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < BN / 16; ++g) {
+        int32_t acc[S][16];
+#pragma unroll
+        for (int o = 0; o < S; ++o) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + g * 16), acc[o]);
+        tmem_ld_wait();
+        double2* cp = reinterpret_cast<double2*>(crow + g * 16);
+        const double2* sp = reinterpret_cast<const double2*>(sc + g * 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double h0 = (double)acc[S - 1][2 * j], h1 = (double)acc[S - 1][2 * j + 1];
+#pragma unroll
+          for (int o = S - 2; o >= 0; --o) {
+            h0 = fma(h0, 0.00390625, (double)acc[o][2 * j]);
+            h1 = fma(h1, 0.00390625, (double)acc[o][2 * j + 1]);
+          }
+          const double2 s2 = sp[j];
+          double2 v = cp[j];
+          v.x = fma(-(sr * s2.x), h0, v.x);
+          v.y = fma(-(sr * s2.y), h1, v.y);
+          cp[j] = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace oz
+}  // namespace gprc

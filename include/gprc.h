@@ -53,11 +53,14 @@ enum {
                              multiple of 4 in 4..32).  0: never (direct differences exactly as R/GPRclass.R:394 writes
                              them); 1 (default): where it measured faster (dot-product kernels, d >= 12); 2: wherever
                              eligible */
-  GPRC_OPT_PREDICT_PATH = 2 /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
+  GPRC_OPT_PREDICT_PATH = 2, /* variance pass v = L^-1 K_star: 0 auto (default), 1 invert L once and multiply
                                (one launch per chunk; best for repeated / small predicts), 2 blocked substitution with
                                two launches per block row (no n^3/3 inversion), 3 the same substitution as one
                                persistent kernel with per-tile progress counters (chosen automatically for >= 18 944
-                               test points when no inverse exists yet) */
+                               test points when no inverse exists yet), 4 the substitution with its O(n^2 m) products
+                               on the INT8 tensor cores (tcgen05, Ozaki digit splitting; FP64 diagonal solves) */
+  GPRC_OPT_OZAKI_DIGITS = 3 /* 8-bit digits per operand entry on path 4: 6, 7 (default; 54 bits below the row /
+                               column maximum) or 8 */
 
 };
 

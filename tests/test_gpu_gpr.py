@@ -166,9 +166,10 @@ def test_large_size_properties(gprc):
     np.testing.assert_allclose(ptrain[:, 0], y[:256] - 0.01 * g.alpha[:256], rtol=0, atol=1e-8)
 
 
-@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("path", [1, 2, 3, 4])
 def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
-    """v = L^-1 K_star either with the explicit inverse (one triangular GEMM) or by blocked substitution."""
+    """v = L^-1 K_star either with the explicit inverse (one triangular GEMM), by blocked substitution in FP64, or by
+    the substitution with its products on the INT8 tensor cores (path 4, ozaki.cuh)."""
     rng = np.random.default_rng(31)
     n, m, D = 700, 450, 5
     X = rng.uniform(-1, 1, (D, n))
@@ -182,6 +183,31 @@ def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
     ok = oracle.cov_func(oracle.rationalquadratic, l=0.8, alpha=1.5)
     ref = oracle.GPR(X, y, 0.05, ok).predict(Xs)
     assert_mean_var(got, ref, ok(Xs, Xs))
+
+
+@pytest.mark.parametrize("digits,tol", [(6, 1e-10), (7, 1e-12), (8, 1e-12)])
+def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tol):
+    """Path 4 against path 2 on the same factor: 1500 training points (12 block rows), polynomial kernel (k** varies
+    per test point, so the per-point exponents differ), more than one 64-point tile per SM."""
+    rng = np.random.default_rng(35)
+    n, m, D = 1500, 148 * 64 + 333, 6
+    X = rng.uniform(-1, 1, (D, n))
+    y = np.sum(X ** 2, axis=0) + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-1.5, 1.5, (D, m))
+    k = gprc.cov_func(gprc.polynomial, sigma=1.0, p=3.0)
+    g = gprc.GPR(X, y, 0.1, k, ctx=ctx)
+    out = {}
+    for path in (2, 4):
+        ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
+        ctx.set_option(gprc._lib.OPT_OZAKI_DIGITS, digits)
+        try:
+            out[path] = g.predict(Xs)
+        finally:
+            ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
+            ctx.set_option(gprc._lib.OPT_OZAKI_DIGITS, 7)
+    kss = (np.sum(Xs * Xs, axis=0) + 1.0) ** 3
+    np.testing.assert_allclose(out[2][:, 0], out[4][:, 0], rtol=1e-13, atol=0)  # the mean does not go through the variance pass
+    assert np.max(np.abs(out[2][:, 1] - out[4][:, 1]) / kss) < tol
 
 
 def test_persistent_and_multi_launch_substitution_are_bitwise_equal(gprc, ctx):
