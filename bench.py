@@ -47,6 +47,13 @@ def parse():
     ap.add_argument("--cpu-sample-m", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--predict-path", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="variance pass (GPRC_OPT_PREDICT_PATH): 0 auto, 1 inverse, 2 FP64 substitution, 3 persistent "
+                         "FP64 substitution, 4 substitution on the INT8 tensor cores")
+    ap.add_argument("--ozaki-digits", type=int, default=7, choices=[6, 7, 8])
+    ap.add_argument("--parity-sample", type=int, default=4096,
+                    help="test points re-predicted through the FP64 substitution (path 2) after the timed run and "
+                         "compared with the timed result")
     ap.add_argument("--train", default="auto", choices=["auto", "replicated", "distributed"],
                     help="N > 1: every rank factorises its own replica, or the factorisation itself is distributed "
                          "(panel-cyclic, NCCL broadcasts) and assembled on every rank; auto = distributed")
@@ -224,6 +231,8 @@ def main():
     import gprc_b200 as g
     ctx = g.Context(local)
     lib = ctx.lib
+    ctx.set_option(g._lib.OPT_PREDICT_PATH, args.predict_path)
+    ctx.set_option(g._lib.OPT_OZAKI_DIGITS, args.ozaki_digits)
     dist_train = world > 1 and args.train in ("auto", "distributed")
     D = None
     if dist_train:
@@ -318,6 +327,7 @@ def main():
     wall = time.perf_counter() - t0
     dev_ms = ctx.elapsed_ms(0, 1)
     timers, launches = ctx.timers()
+    used_path = ctx.last_predict_path()
     if dist_train:
         timers["build_k"], timers["chol"], timers["solve"] = dist_phase["build"], dist_phase["factor"], dist_phase["solve"]
     clocks = sampler.stop() if rank == 0 else None
@@ -328,6 +338,38 @@ def main():
     v = np.empty(min(m_local, 4096))
     ctx.d2h(v, dvar)
     assert np.all(np.isfinite(v)) and v.min() > -1e-8 and v.max() <= 1.0 + 1e-9, (v.min(), v.max())
+
+    # parity of the timed result at full size: the first test points of this rank's shard are predicted again through
+    # the FP64 blocked substitution (path 2) on a fresh factor and compared (mean, variance) with what was timed
+    parity = None
+    ps = min(args.parity_sample, m_local)
+    if ps > 0:
+        got_m, got_v = np.empty(ps), np.empty(ps)
+        ctx.d2h(got_m, dmean)
+        ctx.d2h(got_v, dvar)
+        ctx.set_option(g._lib.OPT_PREDICT_PATH, 2)
+        if dist_train:
+            h = D.fit_replicated(xp, d, n, y, 0.01, spec)[0]
+        else:
+            h = C.c_void_p()
+            lp_, inf_ = C.c_double(0.0), C.c_long(0)
+            g._lib.check(lib.gprc_gpr_fit_dev(ctx.handle, kc, dX, d, n, dy, 0.01, C.byref(h), C.byref(lp_), C.byref(inf_)))
+        dm2, dv2 = ctx.malloc(8 * ps), ctx.malloc(8 * ps)
+        g._lib.check(lib.gprc_gpr_predict_dev(h, dXs, ps, dm2, dv2))
+        ctx.sync()
+        ref_m, ref_v = np.empty(ps), np.empty(ps)
+        ctx.d2h(ref_m, dm2)
+        ctx.d2h(ref_v, dv2)
+        lib.gprc_gpr_free(h)
+        ctx.free(dm2)
+        ctx.free(dv2)
+        ctx.set_option(g._lib.OPT_PREDICT_PATH, args.predict_path)
+        parity = dict(sample=int(ps), against="FP64 blocked substitution (predict path 2) on a fresh factor",
+                      max_abs_dvar=float(np.max(np.abs(got_v - ref_v))),
+                      max_abs_dmean=float(np.max(np.abs(got_m - ref_m))),
+                      max_rel_dvar=float(np.max(np.abs(got_v - ref_v) / np.maximum(np.abs(ref_v), 1e-300))),
+                      tolerance="1e-9 relative on mean and variance (BASELINE.json north_star)")
+        assert parity["max_abs_dvar"] <= 1e-9 and parity["max_abs_dmean"] <= 1e-9 * max(1.0, float(np.max(np.abs(ref_m)))), parity
 
     e2e = None
     if not args.no_e2e:
@@ -352,13 +394,34 @@ def main():
         kname = ("gemm_kernel<TrsmLeftUpdatePolicy> (variance pass v = L^-1 K_star by blocked substitution, K_star^T "
                  "updated in place; column norms fused into gemm_kernel<TrsmLeftDiagPolicy>)") if not timers["trtri"] \
             else "gemm_kernel<TrmmNormPolicy> (variance pass v = (L^-1) K_star, fused column norms)"
+        int8 = None
+        if used_path == 4:
+            # the O(n^2 m) products run as S(S+1)/2 exact INT8 digit products per FP64 product (ozaki.cuh): the kernel's
+            # own roofline is the INT8 tensor pipe.  MEASURED_PEAKS.json has no INT8 figure; INT8 dense is nominally
+            # 2 x bf16 dense on B200 (4.5 vs 2.25 POP/s), so the denominator is 2 x the measured bf16 figure.
+            S = args.ozaki_digits
+            pairs = S * (S + 1) // 2
+            bf16 = None
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+                    bf16 = float(json.load(f)["bf16_tflops_sustained"])
+                src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (of measured; INT8 dense = 2 x bf16 dense nominally)"
+            except Exception:
+                bf16, src = 1400.0, "2 x 1.4 PFLOP/s sustained bf16 (of fallback, B200_PROFILING.md)"
+            int8 = dict(kernel="oz::update_kernel<%d> (tcgen05.mma kind::i8, TMEM accumulators)" % S, digits=S,
+                        int8_products_per_fp64_product=pairs,
+                        achieved_int8_tops=(achieved * pairs) if achieved else None, peak_int8_tops=2 * bf16,
+                        frac_of_int8_peak=(achieved * pairs / (2 * bf16)) if achieved else None, peak_source=src)
+            kname = ("oz::update_kernel<%d> (variance pass v = L^-1 K_star by blocked substitution with the O(n^2 m) "
+                     "products as exact INT8 digit products on tcgen05 / TMEM; FP64 diagonal solves and column norms in "
+                     "gemm_kernel<TrsmLeftDiagPolicy>)" % S)
         roofline = dict(kernel=kname,
                         bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
-                        frac=(achieved / peak_tf) if achieved else None,
+                        frac=(achieved / peak_tf) if achieved else None, int8=int8, predict_path=used_path,
                         # one ncu --set full capture of a mid-sweep launch of this kernel (profiles/README.md):
                         # dram__bytes_read + write = 4.95e9 B for a launch whose algorithmic bytes (V rows read once,
                         # L row panel) are 3.8e9 B
-                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 else None),
+                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 and used_path != 4 else None),
                         traffic_note="bytes of ONE captured launch (grid 148, block row ~197 of 392, 4.37 ms), not per step",
                         peak_source="cuBLAS Dgemm fp64 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json "
                                     "holds no FP64 figure; of measured)",
@@ -366,7 +429,7 @@ def main():
                         share_of_step=var_ms / (sec_per_step * 1e3))
         line = dict(metric=METRIC, value=sec_per_step, unit="s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=sec_per_step * 1e3, higher_is_better=False, scaling="strong", vs_baseline=None,
-                    dtype="f64", data="synthetic", config=config, clocks=clocks, e2e=e2e,
+                    dtype="f64", data="synthetic", config=config, clocks=clocks, e2e=e2e, parity=parity,
                     gpu_launches=int(launches), roofline=roofline,
                     cholesky_tflops=chol_tf, cholesky_frac_of_peak=chol_tf / (peak_tf * (world if dist_train else 1)),
                     test_pts_per_s=m / sec_per_step, wall_s_per_step=wall_per_step, logp=logp,

@@ -23,6 +23,7 @@ GRAD_AS_CODED, GRAD_TEXTBOOK = 0, 1
 OPT_GRAM_DMMA = 1
 OPT_PREDICT_PATH = 2
 OPT_OZAKI_DIGITS = 3
+OPT_INT8_AUTO = 4
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     "gprc_ctx_sync": (C.c_int, [_P]),
     "gprc_ctx_reset_timers": (None, [_P]),
     "gprc_ctx_get_timers": (C.c_int, [_P, c_double_p, c_long_p]),
+    "gprc_ctx_last_predict_path": (C.c_int, [_P]),
     "gprc_ctx_mark": (C.c_int, [_P, C.c_int]),
     "gprc_ctx_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, c_double_p]),
     "gprc_last_error": (C.c_char_p, []),
@@ -174,6 +176,9 @@ class Context:
         launches = C.c_long(0)
         check(self.lib.gprc_ctx_get_timers(self.handle, ms, C.byref(launches)))
         return {n: ms[i] for i, n in enumerate(T_NAMES)}, launches.value
+
+    def last_predict_path(self):
+        return int(self.lib.gprc_ctx_last_predict_path(self.handle))
 
     def mark(self, slot):
         check(self.lib.gprc_ctx_mark(self.handle, slot))

@@ -64,6 +64,8 @@ struct gprc_ctx {
   int opt_gram_dmma = 1;
   int opt_predict_path = 0;
   int opt_ozaki_digits = 7;
+  int opt_int8_auto = 1;
+  int last_predict_path = 0;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};
   // pending (start, stop, phase) events; resolved lazily in gprc_ctx_get_timers so that timing never adds a sync

@@ -354,6 +354,10 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     c->opt_predict_path = value;
     return 0;
   }
+  if (option == GPRC_OPT_INT8_AUTO) {
+    c->opt_int8_auto = value ? 1 : 0;
+    return 0;
+  }
   if (option == GPRC_OPT_OZAKI_DIGITS) {
     GPRC_ARG(value >= 6 && value <= 8);
     c->opt_ozaki_digits = value;
@@ -398,6 +402,8 @@ extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
   if (launches) *launches = c->launches;
   return 0;
 }
+
+extern "C" int gprc_ctx_last_predict_path(gprc_ctx* c) { return c ? c->last_predict_path : 0; }
 
 extern "C" int gprc_ctx_mark(gprc_ctx* c, int slot) {
   GPRC_ARG(c != nullptr && slot >= 0 && slot < 8);
@@ -744,7 +750,7 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   c->launches++;
   for (int i = 0; i < nt; ++i) {
     if (i > 0) {
-      oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 128u, 256u, 0};
+      oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 0, nullptr};
       oz::update_kernel<S><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
       c->launches++;
     }
@@ -803,9 +809,15 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   // launches per block row (whole-wave chunks); 3 = the same substitution as one persistent kernel per chunk.
   // auto: large predicts without an inverse at hand take 3, everything else 1.
   int path = c->opt_predict_path;
-  const bool planned = (path == 0 && !F.W && m >= WAVE_COLS);  // large predict, no inverse at hand: substitution
+  bool planned = (path == 0 && !F.W && m >= WAVE_COLS);  // large predict, no inverse at hand: substitution
+  if (planned && c->opt_int8_auto && F.n_pad >= 4096) {
+    // ... with its products on the INT8 tensor cores once the O(n^2 m) term dominates (2x the FP64 tensor roofline)
+    planned = false;
+    path = 4;
+  }
   if (path == 0 && !planned) path = 1;
   if (path == 1) GPRC_CHECK(ensure_inverse(c, F));
+  c->last_predict_path = planned ? 2 : path;
   PhaseTimer span(c, GPRC_T_PREDICT);
   if (planned) {
     // Mixed plan.  Whole waves of 148 tiles go through the multi-launch substitution (all CTAs sweep the same block row

@@ -12,7 +12,7 @@
 //   * digit products d_a d_b are exact in int32 and are accumulated over k by the tensor core; all pairs with the
 //     same order o = a + b share one TMEM accumulator (S accumulators of 128 x 64 int32 = S * 64 TMEM columns);
 //     pairs with a + b >= S are dropped (they sit below 2^(-8S+2) of the leading term);
-//   * every KC = 8192 k-values (int32 headroom: 7 pairs * 8192 * 2^14 < 2^31) the accumulators are drained:
+//   * every KC = 16384 k-values (int32 headroom: 7 pairs * 16384 * 2^14 < 2^31; 8192 for S = 8) the accumulators are drained:
 //       R -= 2^(eL-6) 2^(eV-6) sum_o acc_o 256^-o     (Horner in FP64, one rounding per term).
 //   S = 7 carries 54 bits below the row / column maximum: |var - var_fp64| ~ 1e-14 at n = 1024 (tools/oz_sim.py).
 //
@@ -35,18 +35,20 @@ namespace oz {
 constexpr int BM = 128;    // L rows per tile = one block row of the substitution
 constexpr int BN = 64;     // test points per tile
 constexpr int BK = 32;     // k per stage = K of one tcgen05.mma kind::i8
-constexpr int KC = 8192;   // drain interval (int32 headroom)
 constexpr int A_TILE = BM * BK;  // 4096 B
 constexpr int B_TILE = BN * BK;  // 2048 B
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;
+constexpr int DRAIN_STAGING_BYTES = 4 * 32 * 9 * 8;  // per drain warp: 32 rows x 8 columns of FP64, row pitch 9
 
 template <int S>
 struct Cfg {
   static_assert(S >= 1 && S <= 8, "1..8 digits");
   static constexpr int STAGE_BYTES = S * (A_TILE + B_TILE);
-  static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 8 ? 8 : (220 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+  static constexpr int STAGES = (217 * 1024) / STAGE_BYTES > 8 ? 8 : (217 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + DRAIN_STAGING_BYTES + 256;
+  // drain interval: the order with the most pairs (S of them) must stay below 2^31: S * KC * 2^14 < 2^31
+  static constexpr int KC = (S <= 7) ? 16384 : 8192;
 };
 
 __host__ __device__ __forceinline__ int tile_off(int r, int k) {
@@ -281,16 +283,38 @@ struct UpdateParams {
   int i;   // block row
   int KB;  // k blocks per row of tiles = n_pad / 32
   int* error;
-  uint32_t lbo, sbo;  // descriptor strides (128 / 256 for the layout above)
-  int dbg;            // tools/oz_test only: 1 = no MMA (feed rate), 2 = no TMA (MMA rate), 4 = one bulk copy per digit
+  int dbg;            // tools/oz_test only: 1 = no MMA (feed rate), 2 = no TMA (MMA rate)
+  long long* trace;   // tools/oz_test only: clock64 of CTA 0 at [kt][0] producer issues, [1] stage landed, [2] MMAs issued
 };
+
+// one lane of a converged warp (the issuing lane of the TMA / tcgen05 instructions); elect.sync keeps the branch
+// warp-uniform for the compiler, so descriptors stay in uniform registers (an `if (lane == 0)` region makes every
+// UTCIMMA an ELECT / branch loop of its own)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 
 // R_i[128 x 64] -= L[i, <i] V[<i, tile]   one CTA per 64-test-point tile
 template <int S>
 __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p) {
   using C = Cfg<S>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::STAGES * C::STAGE_BYTES);
+  double* stg_all = reinterpret_cast<double*>(smem_raw + C::STAGES * C::STAGE_BYTES);  // drain staging, 4 x [32][9]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::STAGES * C::STAGE_BYTES + DRAIN_STAGING_BYTES);
   uint64_t* empty = full + C::STAGES;
   uint64_t* tmem_full = empty + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
@@ -298,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tc = blockIdx.x;
   const int KT = 4 * p.i;                      // k-steps
-  constexpr int KT_CHUNK = KC / BK;            // k-steps per drain
+  constexpr int KT_CHUNK = C::KC / BK;         // k-steps per drain
   const int nchunks = (KT + KT_CHUNK - 1) / KT_CHUNK;
 
   if (threadIdx.x == 0) {
@@ -318,35 +342,33 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== producer =====
-    if (lane == 0) {
-      const int8_t* a_src = p.Ls + (long)p.i * p.KB * (long)(S * A_TILE);
-      const int8_t* b_src = p.Vs + (long)tc * p.KB * (long)(S * B_TILE);
-      for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % C::STAGES;
-        if (kt >= C::STAGES) mbar_wait_guarded(smem_u32(empty + s), ((kt / C::STAGES) - 1) & 1, p.error, 16);
+    // ===== producer (whole warp loops, one elected lane issues) =====
+    const int8_t* a_src = p.Ls + (long)p.i * p.KB * (long)(S * A_TILE);
+    const int8_t* b_src = p.Vs + (long)tc * p.KB * (long)(S * B_TILE);
+    for (int kt = 0; kt < KT; ++kt) {
+      const int s = kt % C::STAGES;
+      if (kt >= C::STAGES) mbar_wait_guarded(smem_u32(empty + s), ((kt / C::STAGES) - 1) & 1, p.error, 16);
+      if (elect_one()) {
         const uint32_t bar = smem_u32(full + s);
         const uint32_t dst = smem_u32(smem_raw + s * C::STAGE_BYTES);
+        if (p.trace && tc == 0 && kt < 512) p.trace[kt * 4 + 0] = clock64();
         if (p.dbg & 2) {
           mbar_arrive(bar);
-          continue;
+        } else {
+          mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+          bulk_g2s(dst, a_src + (long)kt * (S * A_TILE), S * A_TILE, bar);
+          bulk_g2s(dst + S * A_TILE, b_src + (long)kt * (S * B_TILE), S * B_TILE, bar);
         }
-        mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
-        if (p.dbg & 4) {
-          for (int q = 0; q < S; ++q) {
-            bulk_g2s(dst + q * A_TILE, a_src + (long)kt * (S * A_TILE) + q * A_TILE, A_TILE, bar);
-            bulk_g2s(dst + S * A_TILE + q * B_TILE, b_src + (long)kt * (S * B_TILE) + q * B_TILE, B_TILE, bar);
-          }
-          continue;
-        }
-        bulk_g2s(dst, a_src + (long)kt * (S * A_TILE), S * A_TILE, bar);
-        bulk_g2s(dst + S * A_TILE, b_src + (long)kt * (S * B_TILE), S * B_TILE, bar);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: one elected lane waits, issues and commits (the other lanes idle until the final barrier) =====
+    // The wait for the NEXT stage sits in the middle of this stage's products: the tensor pipe still has queued MMAs
+    // while the issuing lane pays the try_wait / fence latency, so the pipe does not drain between k-steps.
+    if (elect_one()) {
       constexpr uint32_t idesc = instr_desc_i8(BM, BN);
+      constexpr int NPAIRS = S * (S + 1) / 2, HALF = NPAIRS / 2;
       int kt = 0;
       for (int c = 0; c < nchunks; ++c) {
         if (c > 0) {
@@ -354,62 +376,81 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
           tc_fence_after();
         }
         const int kt_end = min(KT, (c + 1) * KT_CHUNK);
+        mbar_wait_guarded(smem_u32(full + kt % C::STAGES), (kt / C::STAGES) & 1, p.error, 64);
+        tc_fence_after();
         for (bool first = true; kt < kt_end; ++kt, first = false) {
           const int s = kt % C::STAGES;
-          mbar_wait_guarded(smem_u32(full + s), (kt / C::STAGES) & 1, p.error, 64);
-          tc_fence_after();
+          if (p.trace && tc == 0 && kt < 512) p.trace[kt * 4 + 1] = clock64();
           if (p.dbg & 1) {
+            if (kt + 1 < kt_end) mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
             mbar_arrive(smem_u32(empty + s));
-            continue;
-          }
-          const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES), b0 = a0 + S * A_TILE;
+          } else {
+            const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES);
+            const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + S * A_TILE, 128, 256);
+            int pair = 0;
 #pragma unroll
-          for (int a = 0; a < S; ++a) {
-            const uint64_t ad = smem_desc(a0 + a * A_TILE, p.lbo, p.sbo);
+            for (int a = 0; a < S; ++a) {
 #pragma unroll
-            for (int b = 0; b < S - a; ++b) {
-              const uint64_t bd = smem_desc(b0 + b * B_TILE, p.lbo, p.sbo);
-              // the first product into accumulator a + b of this chunk is (0, a + b) at the chunk's first k-step
-              mma_i8(tmem_base + (uint32_t)((a + b) * BN), ad, bd, idesc, (!first || a > 0) ? 1u : 0u);
+              for (int b = 0; b < S - a; ++b, ++pair) {
+                if (pair == HALF && kt + 1 < kt_end) {
+                  mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
+                  tc_fence_after();
+                }
+                // the first product into accumulator a + b of this chunk is (0, a + b) at the chunk's first k-step
+                mma_i8(tmem_base + (uint32_t)((a + b) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                       bd0 + (uint64_t)(b * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+              }
             }
+            tc_commit(smem_u32(empty + s));  // stage s may be refilled once these MMAs have read it
           }
-          tc_commit(smem_u32(empty + s));  // stage s may be refilled once these MMAs have read it
+          if (kt + 1 == kt_end) tc_commit(smem_u32(tmem_full));  // accumulators of chunk c are complete
+          if (p.trace && tc == 0 && kt < 512) p.trace[kt * 4 + 2] = clock64();
         }
-        tc_commit(smem_u32(tmem_full));  // accumulators of chunk c are complete
       }
     }
+    __syncwarp();
   } else {
-    // ===== drain: TMEM -> registers -> R (in place) =====
+    // ===== drain: TMEM -> registers -> (transpose through shared memory) -> R in place, coalesced =====
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;       // row of the tile = TMEM lane
     const double sr = p.scale_row[(long)p.i * BM + row];
-    double* crow = p.T + (long)tc * BN + ((long)p.i * BM + row) * p.ldt;
     const double* sc = p.scale_col + (long)tc * BN;
+    double* stg = stg_all + q * (32 * 9);
+    // rows of R this lane touches when the warp walks the tile 4 rows x 8 columns at a time
+    double* cbase = p.T + (long)tc * BN + ((long)p.i * BM + q * 32 + (lane >> 3)) * p.ldt + (lane & 7);
+    {  // pull this tile of R into L2 while the first chunk is being multiplied
+      const double* prow = p.T + (long)tc * BN + ((long)p.i * BM + row) * p.ldt;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prefetch_l2(prow + j * 16);
+    }
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait_guarded(smem_u32(tmem_full), c & 1, p.error, 128);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < BN / 16; ++g) {
-        int32_t acc[S][16];
+      for (int g = 0; g < BN / 8; ++g) {
+        int32_t acc[S][8];
 #pragma unroll
-        for (int o = 0; o < S; ++o) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + g * 16), acc[o]);
+        for (int o = 0; o < S; ++o) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + g * 8), acc[o]);
+        double cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = cbase[(long)(it * 4) * p.ldt + g * 8];  // in flight during the combine
+        double scv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scv[j] = __ldg(sc + g * 8 + j);
         tmem_ld_wait();
-        double2* cp = reinterpret_cast<double2*>(crow + g * 16);
-        const double2* sp = reinterpret_cast<const double2*>(sc + g * 16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          double h0 = (double)acc[S - 1][2 * j], h1 = (double)acc[S - 1][2 * j + 1];
+          double h = (double)acc[S - 1][j];
 #pragma unroll
-          for (int o = S - 2; o >= 0; --o) {
-            h0 = fma(h0, 0.00390625, (double)acc[o][2 * j]);
-            h1 = fma(h1, 0.00390625, (double)acc[o][2 * j + 1]);
-          }
-          const double2 s2 = sp[j];
-          double2 v = cp[j];
-          v.x = fma(-(sr * s2.x), h0, v.x);
-          v.y = fma(-(sr * s2.y), h1, v.y);
-          cp[j] = v;
+          for (int o = S - 2; o >= 0; --o) h = fma(h, 0.00390625, (double)acc[o][j]);
+          stg[lane * 9 + j] = (sr * scv[j]) * h;
         }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] -= stg[(it * 4 + (lane >> 3)) * 9 + (lane & 7)];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cbase[(long)(it * 4) * p.ldt + g * 8] = cur[it];
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -59,8 +59,10 @@ enum {
                                persistent kernel with per-tile progress counters (chosen automatically for >= 18 944
                                test points when no inverse exists yet), 4 the substitution with its O(n^2 m) products
                                on the INT8 tensor cores (tcgen05, Ozaki digit splitting; FP64 diagonal solves) */
-  GPRC_OPT_OZAKI_DIGITS = 3 /* 8-bit digits per operand entry on path 4: 6, 7 (default; 54 bits below the row /
+  GPRC_OPT_OZAKI_DIGITS = 3, /* 8-bit digits per operand entry on path 4: 6, 7 (default; 54 bits below the row /
                                column maximum) or 8 */
+  GPRC_OPT_INT8_AUTO = 4 /* 1 (default): the automatic choice takes path 4 where it takes the substitution today
+                            (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
 
 };
 
@@ -102,6 +104,8 @@ int gprc_ctx_get_timers(gprc_ctx* ctx, double* ms /* GPRC_T_COUNT */, long* kern
 /* user event pair on the library's stream: device-side timing of an arbitrary region (bench.py) */
 int gprc_ctx_mark(gprc_ctx* ctx, int slot /* 0..7 */);
 int gprc_ctx_elapsed_ms(gprc_ctx* ctx, int slot_start, int slot_stop, double* ms);
+/* variance-pass path (1..4, see GPRC_OPT_PREDICT_PATH) the most recent predict on this context resolved to; 0 = none yet */
+int gprc_ctx_last_predict_path(gprc_ctx* ctx);
 const char* gprc_last_error(void);
 int gprc_version(void);
 

@@ -80,7 +80,10 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   printf("split done, overflow flag = %d\n", herr);
 
   CK(cudaFuncSetAttribute(oz::update_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
-  oz::UpdateParams p{dLs, dVs, dsr, dsc, dT, mc, i, (int)KB, derr, lbo, sbo, dbg};
+  long long* dtrace = nullptr;
+  CK(cudaMalloc(&dtrace, 512 * 4 * 8));
+  CK(cudaMemset(dtrace, 0, 512 * 4 * 8));
+  oz::UpdateParams p{dLs, dVs, dsr, dsc, dT, mc, i, (int)KB, derr, dbg, nullptr};
   printf("S=%d n=%ld mc=%ld i=%d stages=%d smem=%d lbo=%u sbo=%u\n", S, n, mc, i, oz::Cfg<S>::STAGES,
          oz::Cfg<S>::SMEM_BYTES, lbo, sbo);
 
@@ -98,6 +101,18 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
     ms /= reps;
+    if (dbg & 32) {
+      p.trace = dtrace;
+      oz::update_kernel<S><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> tr(512 * 4);
+      CK(cudaMemcpy(tr.data(), dtrace, 512 * 4 * 8, cudaMemcpyDeviceToHost));
+      const long long t0 = tr[0];
+      printf("trace of CTA 0 (clk since first producer issue): kt  producer_issue  stage_landed  mmas_issued\n");
+      for (int kt = 0; kt < 4 * i && kt < 512; ++kt)
+        if (kt < 24 || (kt >= 200 && kt < 216) || (kt >= 250 && kt < 266))
+          printf("  %3d %9lld %9lld %9lld\n", kt, tr[kt * 4] - t0, tr[kt * 4 + 1] - t0, tr[kt * 4 + 2] - t0);
+    }
     const double K = 128.0 * i, flops = 2.0 * 128 * mc * K;
     long long* dclk;
     CK(cudaMalloc(&dclk, 16));
