@@ -606,12 +606,14 @@ static int ensure_inverse(gprc_ctx* c, FactorState& F) {
 
 constexpr long WAVE_COLS = 148L * NB;  // test points of one full wave of 128-wide tiles on 148 SMs
 
-static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m, double max_bytes = 8.0e9) {
+static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m, double max_bytes = 8.0e9,
+                            double extra_bytes_per_col = 0.0) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   long want = round_up(std::max<long>(m, 1), NB);
   // per test point: Ks column + partial rows
-  const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1);
+  // (+ the INT8 path's digit planes of V, allocated by its variance pass)
+  const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1) + extra_bytes_per_col;
   const double budget = std::min(max_bytes, 0.45 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
   long cap = (long)(budget / per_col) / NB * NB;
   cap = std::max<long>(cap, NB);
@@ -765,6 +767,14 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   return 0;
 }
 
+static int oz_factor_digits_any(gprc_ctx* c, FactorState& F) {
+  switch (c->opt_ozaki_digits) {
+    case 6: return oz_factor_digits<6>(c, F);
+    case 8: return oz_factor_digits<8>(c, F);
+    default: return oz_factor_digits<7>(c, F);
+  }
+}
+
 static int variance_pass_ozaki(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur, long mcur_pad) {
   switch (c->opt_ozaki_digits) {
     case 6: return variance_pass_ozaki_t<6>(c, F, ws, mcur, mcur_pad);
@@ -860,7 +870,10 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   if (path == 4) {
     // INT8 substitution: whole-wave chunks like path 2; the overflow / watchdog flag is read after every chunk and a
     // flagged chunk (a K_star that violates |v| <= sqrt(k**), i.e. not a covariance of this model) is redone in FP64
-    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 12.0e9));
+    // Big chunks: the CTAs of this path are independent (no lockstep sweep to preserve), so many waves per launch
+    // amortise the per-block-row launches and leave one short tail instead of one per 148-tile chunk.
+    GPRC_CHECK(oz_factor_digits_any(c, F));  // before sizing the workspace: the digit planes of L take n_pad^2 S bytes
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 75.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad));
     for (long c0 = 0; c0 < m; c0 += ws.mc) {
       const long mcur = std::min(ws.mc, m - c0);
       GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 4, dmean, dvar));
