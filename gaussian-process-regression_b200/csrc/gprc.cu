@@ -730,7 +730,7 @@ template <int S>
 static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur, long mcur_pad) {
   static bool configured[64] = {false};
   if (!configured[c->device & 63]) {
-    GPRC_CUDA(cudaFuncSetAttribute(oz::update_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    GPRC_CUDA(cudaFuncSetAttribute(oz::update_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
     configured[c->device & 63] = true;
   }
   GPRC_CHECK(oz_factor_digits<S>(c, F));
@@ -753,7 +753,7 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   for (int i = 0; i < nt; ++i) {
     if (i > 0) {
       oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 0, nullptr};
-      oz::update_kernel<S><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
+      oz::update_kernel<S, false><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
       c->launches++;
     }
     TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};

@@ -222,6 +222,23 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with A taken from tensor memory (128 lanes x 8 columns hold the 128 x 32 int8 tile): only B is read from shared
+// memory by the MMA
+__device__ __forceinline__ void mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory (canonical K-major tile, 128 rows x 32 bytes) -> tensor memory (128 lanes x 256 bits); executes in issue
+// order with the tcgen05.mma of the same thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // mbarrier arrives once all tcgen05 operations issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -283,7 +300,7 @@ struct UpdateParams {
   int i;   // block row
   int KB;  // k blocks per row of tiles = n_pad / 32
   int* error;
-  int dbg;            // tools/oz_test only: 1 = no MMA (feed rate), 2 = no TMA (MMA rate)
+  int dbg;            // tools/oz_test only: 1 = no MMA (feed rate), 2 = no TMA (MMA rate), 8 = products grouped by order
   long long* trace;   // tools/oz_test only: clock64 of CTA 0 at [kt][0] producer issues, [1] stage landed, [2] MMAs issued
 };
 
@@ -309,8 +326,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
 }
 
 // R_i[128 x 64] -= L[i, <i] V[<i, tile]   one CTA per 64-test-point tile
-template <int S>
+// TS: the digit tiles of L are first copied shared -> tensor memory (tcgen05.cp, S * 8 columns behind the accumulators)
+// and the products take A from there, so that each MMA reads only its 2 KB B tile from shared memory (the SS form
+// re-reads the 4 KB A tile for every one of the S (S + 1) / 2 products and is bound by that, profiles/README.md).
+template <int S, bool TS>
 __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p) {
+  static_assert(!TS || S * (BN + 8) <= TMEM_COLS, "no room for the A tiles in tensor memory");
   using C = Cfg<S>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stg_all = reinterpret_cast<double*>(smem_raw + C::STAGES * C::STAGE_BYTES);  // drain staging, 4 x [32][9]
@@ -387,6 +408,31 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
           } else {
             const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES);
             const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + S * A_TILE, 128, 256);
+            const uint32_t a_tmem = tmem_base + (uint32_t)(S * BN);
+            if (TS) {
+#pragma unroll
+              for (int a = 0; a < S; ++a) tmem_cp_128x256b(a_tmem + (uint32_t)(a * 8), ad0 + (uint64_t)(a * (A_TILE >> 4)));
+            }
+            if (p.dbg & 8) {  // experiment: products grouped by accumulator (order-major)
+#pragma unroll
+              for (int o = 0; o < S; ++o)
+#pragma unroll
+                for (int a = 0; a <= o; ++a) {
+                  if (TS)
+                    mma_i8_ts(tmem_base + (uint32_t)(o * BN), a_tmem + (uint32_t)(a * 8),
+                              bd0 + (uint64_t)((o - a) * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+                  else
+                    mma_i8(tmem_base + (uint32_t)(o * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                           bd0 + (uint64_t)((o - a) * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+                }
+              if (kt + 1 < kt_end) {
+                mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
+                tc_fence_after();
+              }
+              tc_commit(smem_u32(empty + s));
+              if (kt + 1 == kt_end) tc_commit(smem_u32(tmem_full));
+              continue;
+            }
             int pair = 0;
 #pragma unroll
             for (int a = 0; a < S; ++a) {
@@ -397,8 +443,12 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
                   tc_fence_after();
                 }
                 // the first product into accumulator a + b of this chunk is (0, a + b) at the chunk's first k-step
-                mma_i8(tmem_base + (uint32_t)((a + b) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
-                       bd0 + (uint64_t)(b * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+                if (TS)
+                  mma_i8_ts(tmem_base + (uint32_t)((a + b) * BN), a_tmem + (uint32_t)(a * 8),
+                            bd0 + (uint64_t)(b * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+                else
+                  mma_i8(tmem_base + (uint32_t)((a + b) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                         bd0 + (uint64_t)(b * (B_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
               }
             }
             tc_commit(smem_u32(empty + s));  // stage s may be refilled once these MMAs have read it

@@ -225,3 +225,18 @@ def test_plain_c_client_reproduces_known_answers(tmp_path):
     r = subprocess.run([exe], env=dict(os.environ, LD_LIBRARY_PATH=PKG), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert "all known answers reproduced through the C ABI" in r.stdout
+
+
+def test_int8_digit_arithmetic_host_selftest():
+    """csrc/ozaki.cuh: the fixed-point digit split used by the INT8 variance pass, compiled for the host by
+    tools/oz_test: exact reconstruction, int8 digit range, overflow flag, int32 headroom of the drain interval,
+    shared-memory / TMEM budgets -- for 6, 7 and 8 digits."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "oz_test")
+    if not os.path.exists(tool):
+        import __graft_entry__ as ge
+        ge.build()
+    out = subprocess.run([tool, "digits"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" 0 failures") == 5, out.stdout

@@ -1,7 +1,7 @@
 // oz_test.cu -- standalone check of the INT8 (tcgen05) substitution update of csrc/ozaki.cuh against (a) a host
 // emulation of exactly the same digit arithmetic and (b) the plain FP64 product; plus a timing mode.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/oz_test tools/oz_test.cu
-//   tools/oz_test check <S> <n> <mc> <i> [lbo sbo]        tools/oz_test time <S> <n> <mc> <i>
+//   tools/oz_test check|time <S> <n> <mc> <i> [ts 0 [dbg]]   (ts = 1: A operand from tensor memory)   tools/oz_test digits
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -36,7 +36,7 @@ __global__ void clock_probe(long long* out) {
   out[1] = (long long)(t1 - t0);
 }
 
-template <int S>
+template <int S, bool TS>
 static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, int dbg) {
   const long n_pad = n, KB = n_pad / 32;
   std::mt19937_64 rng(12345);
@@ -79,23 +79,23 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
   printf("split done, overflow flag = %d\n", herr);
 
-  CK(cudaFuncSetAttribute(oz::update_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(oz::update_kernel<S, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
   long long* dtrace = nullptr;
   CK(cudaMalloc(&dtrace, 512 * 4 * 8));
   CK(cudaMemset(dtrace, 0, 512 * 4 * 8));
   oz::UpdateParams p{dLs, dVs, dsr, dsc, dT, mc, i, (int)KB, derr, dbg, nullptr};
-  printf("S=%d n=%ld mc=%ld i=%d stages=%d smem=%d lbo=%u sbo=%u\n", S, n, mc, i, oz::Cfg<S>::STAGES,
-         oz::Cfg<S>::SMEM_BYTES, lbo, sbo);
+  printf("S=%d %s n=%ld mc=%ld i=%d stages=%d smem=%d\n", S, TS ? "TS (A in tensor memory)" : "SS", n, mc, i,
+         oz::Cfg<S>::STAGES, oz::Cfg<S>::SMEM_BYTES);
 
   if (timing) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    for (int w = 0; w < 100; ++w) oz::update_kernel<S><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+    for (int w = 0; w < 100; ++w) oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
     CK(cudaDeviceSynchronize());
     const int reps = 20;
     cudaEventRecord(a);
-    for (int w = 0; w < reps; ++w) oz::update_kernel<S><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+    for (int w = 0; w < reps; ++w) oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
     cudaEventRecord(b);
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -103,7 +103,7 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     ms /= reps;
     if (dbg & 32) {
       p.trace = dtrace;
-      oz::update_kernel<S><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+      oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
       CK(cudaDeviceSynchronize());
       std::vector<long long> tr(512 * 4);
       CK(cudaMemcpy(tr.data(), dtrace, 512 * 4 * 8, cudaMemcpyDeviceToHost));
@@ -120,13 +120,13 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     long long hclk[2];
     CK(cudaMemcpy(hclk, dclk, 16, cudaMemcpyDeviceToHost));
     const double mhz = (double)hclk[0] / (double)hclk[1] * 1e3;
-    printf("update_kernel<%d> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
-           "%.0f clk per k-step\n", S, dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
+    printf("update_kernel<%d,%s> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
+           "%.0f clk per k-step\n", S, TS ? "TS" : "SS", dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
            ms * 1e-3 * mhz * 1e6 / (4.0 * i) / ((mc / 64 + 147) / 148));
     return 0;
   }
 
-  oz::update_kernel<S><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+  oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("update kernel failed: %s\n", cudaGetErrorString(e));
@@ -193,32 +193,139 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
       }
     }
   }
-  printf("RESULT S=%d i=%d lbo=%u sbo=%u: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
-         S, i, lbo, sbo, herr, max_emul, bad, 128 * mc, max_fp64, max_ref, bad == 0 ? "  OK" : "  FAIL");
+  printf("RESULT S=%d %s i=%d: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
+         S, TS ? "TS" : "SS", i, herr, max_emul, bad, 128 * mc, max_fp64, max_ref, bad == 0 ? "  OK" : "  FAIL");
   return bad == 0 ? 0 : 1;
 }
 
+// tensor-pipe rate probe: one CTA per SM issues `count` int8 MMAs of shape 128 x N x 32 from (uninitialised) shared
+// memory, rotating over `rot` accumulators and `nsrc` operand tiles; reports clocks per MMA
+template <int N, bool TS>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int count, int rot, int nsrc, long long* out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) oz::tmem_alloc(smem_u32(&slot), 512);
+  oz::tc_fence_before();
+  __syncthreads();
+  oz::tc_fence_after();
+  const uint32_t tb = slot;
+  if (warp == 0 && oz::elect_one()) {
+    const uint32_t idesc = oz::instr_desc_i8(128, N);
+    const uint32_t s0 = smem_u32(sm);
+    const long long t0 = clock64();
+    for (int it = 0; it < count; ++it) {
+      const int r = it % rot, q = it % nsrc;
+      const uint64_t ad = oz::smem_desc(s0 + q * 4096, 128, 256), bd = oz::smem_desc(s0 + 65536 + q * (N * 32), 128, 256);
+      if (TS) oz::mma_i8_ts(tb + r * N, tb + 448 + (q % 8) * 8, bd, idesc, 1u);
+      else oz::mma_i8(tb + r * N, ad, bd, idesc, 1u);
+    }
+    oz::tc_commit(smem_u32(&bar));
+    oz::mbar_wait_guarded(smem_u32(&bar), 0, (int*)out + 8, 1);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  oz::tc_fence_before();
+  __syncthreads();
+  oz::tc_fence_after();
+  if (warp == 0) {
+    __syncwarp();
+    oz::tmem_dealloc(tb, 512);
+  }
+}
+
+template <int N, bool TS>
+static void mma_rate(int rot, int nsrc) {
+  long long* d;
+  cudaMalloc(&d, 128);
+  cudaMemset(d, 0, 128);
+  const int smem = 65536 + 8 * N * 32 + 1024, count = 20000;
+  cudaFuncSetAttribute(mma_rate_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int w = 0; w < 3; ++w) mma_rate_kernel<N, TS><<<148, 128, smem>>>(count, rot, nsrc, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  printf("mma rate: 128x%dx32 int8 %s, %d accumulators, %d operand tiles: %.1f clk per MMA (floor %d) %s\n", N, TS ? "TS" : "SS",
+         rot, nsrc, (double)h / count, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d);
+}
+
+// host-only self-test of the digit arithmetic (no GPU): sum_t digit_t 256^(S-1-t) reproduces the fixed-point value
+// exactly, digits stay in int8 range, the per-order int32 headroom of the drain interval holds in the worst case
+template <int S>
+static int digits_selftest() {
+  std::mt19937_64 rng(7);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  long bad = 0;
+  for (int rep = 0; rep < 200000; ++rep) {
+    const int e = (int)(rng() % 40) - 20;
+    double x = ldexp(U(rng), e);
+    if (rep % 1000 == 0) x = ldexp(rep % 2000 ? 1.0 : -1.0, e) * (1.0 - 1e-16);  // the edges of the range
+    if (rep % 1000 == 1) x = 0.0;
+    bool ovf = false;
+    const long long X = oz::to_fixed<S>(x, e, &ovf);
+    const long long Y = oz::biased<S>(X);
+    long long rec = 0;
+    for (int s = 0; s < S; ++s) {
+      const int dgt = oz::digit<S>(Y, s);
+      if (dgt < -128 || dgt > 127) ++bad;
+      rec = rec * 256 + dgt;
+    }
+    if (ovf || rec != X) ++bad;
+    if (fabs(ldexp((double)X, e - (8 * S - 2)) - x) > ldexp(1.0, e - (8 * S - 2))) ++bad;  // <= 1 unit of the last digit
+  }
+  bool ovf = false;
+  oz::to_fixed<S>(2.0, 0, &ovf);  // |x| >= 1.9 * 2^e must raise the flag
+  if (!ovf) ++bad;
+  if ((long long)S * oz::Cfg<S>::KC * 16384LL >= (1LL << 31)) ++bad;  // all S pairs of one order at (-128)^2 for KC steps
+  if (oz::Cfg<S>::SMEM_BYTES > 227 * 1024 || S * oz::BN > oz::TMEM_COLS) ++bad;
+  printf("digits S=%d: %ld failures (KC=%d, stages=%d, smem=%d B)\n", S, bad, oz::Cfg<S>::KC, oz::Cfg<S>::STAGES,
+         oz::Cfg<S>::SMEM_BYTES);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "digits")
+    return digits_selftest<6>() | digits_selftest<7>() | digits_selftest<8>() | digits_selftest<1>() | digits_selftest<2>();
+  if (argc >= 2 && std::string(argv[1]) == "rate") {
+    mma_rate<64, false>(1, 1);
+    mma_rate<64, false>(7, 1);
+    mma_rate<64, false>(7, 7);
+    mma_rate<64, true>(1, 1);
+    mma_rate<64, true>(7, 7);
+    mma_rate<128, false>(1, 1);
+    mma_rate<128, false>(3, 7);
+    mma_rate<128, true>(3, 7);
+    mma_rate<256, false>(1, 1);
+    mma_rate<256, false>(1, 7);
+    mma_rate<256, true>(1, 7);
+    return 0;
+  }
   if (argc < 6) {
-    printf("usage: oz_test check|time S n mc i [lbo sbo]\n");
+    printf("usage: oz_test check|time S n mc i [ts 0 [dbg]] | oz_test digits\n");
     return 64;
   }
   const bool timing = std::string(argv[1]) == "time";
   const int S = atoi(argv[2]);
   const long n = atol(argv[3]), mc = atol(argv[4]);
   const int i = atoi(argv[5]);
-  const uint32_t lbo = argc > 7 ? (uint32_t)atoi(argv[6]) : 128u, sbo = argc > 7 ? (uint32_t)atoi(argv[7]) : 256u;
+  const uint32_t lbo = argc > 7 ? (uint32_t)atoi(argv[6]) : 0u, sbo = 0u;  // argv[6] = 1 selects the TS kernel
   const int dbg = argc > 8 ? atoi(argv[8]) : 0;
   if (n % 128 || mc % 64 || i < 1 || i >= n / 128) {
     printf("bad sizes\n");
     return 64;
   }
   switch (S) {
-    case 1: return run<1>(timing, n, mc, i, lbo, sbo, dbg);
-    case 2: return run<2>(timing, n, mc, i, lbo, sbo, dbg);
-    case 6: return run<6>(timing, n, mc, i, lbo, sbo, dbg);
-    case 7: return run<7>(timing, n, mc, i, lbo, sbo, dbg);
-    case 8: return run<8>(timing, n, mc, i, lbo, sbo, dbg);
+    case 1: return (lbo == 1 ? run<1, true>(timing, n, mc, i, lbo, sbo, dbg) : run<1, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 2: return (lbo == 1 ? run<2, true>(timing, n, mc, i, lbo, sbo, dbg) : run<2, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 6: return (lbo == 1 ? run<6, true>(timing, n, mc, i, lbo, sbo, dbg) : run<6, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 7: return (lbo == 1 ? run<7, true>(timing, n, mc, i, lbo, sbo, dbg) : run<7, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 8: return run<8, false>(timing, n, mc, i, lbo, sbo, dbg);
   }
   printf("S must be 1, 2, 6, 7 or 8\n");
   return 64;
