@@ -10,7 +10,11 @@ rank, and every rank factorises its own replica (no data-path collective; total 
   e2e     the same through the host API (GPR(X, y, noise, k); $predict(X_star)) with pinned HOST buffers: H2D of
           X, y, X_star and D2H of mean/var inside the timed region
   roofline      the dominant kernel (variance pass: V = L^-1 K_star, fused column norms) against the FP64 tensor
-                peak measured live with cuBLAS Dgemm (MEASURED_PEAKS.json has no FP64 figure)
+                peak measured live with cuBLAS Dgemm (MEASURED_PEAKS.json has no FP64 figure).  With the INT8
+                tensor-core pass (the default at this size) the fraction exceeds 1; roofline.int8 states the same
+                time against the INT8 pipe (2 x the measured bf16 rate)
+  parity        the first 4096 test points of the timed result re-predicted through the FP64 substitution on a
+                fresh factor; asserted within the north-star tolerance (1e-9)
   cpu_baseline  the oracle (NumPy/SciPy/OpenBLAS restatement of the reference's R path) on the host cores, on a
                 bounded sample scaled by flop count to the full job (R is not installed: kind = "port")
 
@@ -421,8 +425,11 @@ def main():
                         # one ncu --set full capture of a mid-sweep launch of this kernel (profiles/README.md):
                         # dram__bytes_read + write = 4.95e9 B for a launch whose algorithmic bytes (V rows read once,
                         # L row panel) are 3.8e9 B
-                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 and used_path != 4 else None),
-                        traffic_note="bytes of ONE captured launch (grid 148, block row ~197 of 392, 4.37 ms), not per step",
+                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 and used_path != 4 else (1.1167e9 if used_path == 4 else None)),
+                        traffic_note=("dram bytes of ONE captured launch of oz::update_kernel<7> (ncu --set full, K = 16 256, "
+                                      "9472 test points; algorithmic bytes of that launch 1.10e9), not per step; "
+                                      "profiles/README.md") if used_path == 4 else
+                                     "bytes of ONE captured launch (grid 148, block row ~197 of 392, 4.37 ms), not per step",
                         peak_source="cuBLAS Dgemm fp64 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json "
                                     "holds no FP64 figure; of measured)",
                         algorithmic_flops_per_step=flops_var, ms_per_step=var_ms,
