@@ -55,6 +55,8 @@ def parse():
                     help="variance pass (GPRC_OPT_PREDICT_PATH): 0 auto, 1 inverse, 2 FP64 substitution, 3 persistent "
                          "FP64 substitution, 4 substitution on the INT8 tensor cores")
     ap.add_argument("--ozaki-digits", type=int, default=7, choices=[6, 7, 8])
+    ap.add_argument("--int8-tile", type=int, default=64, choices=[64, 128],
+                    help="test points per CTA of the INT8 pass (GPRC_OPT_INT8_TILE)")
     ap.add_argument("--parity-sample", type=int, default=4096,
                     help="test points re-predicted through the FP64 substitution (path 2) after the timed run and "
                          "compared with the timed result")
@@ -237,6 +239,7 @@ def main():
     lib = ctx.lib
     ctx.set_option(g._lib.OPT_PREDICT_PATH, args.predict_path)
     ctx.set_option(g._lib.OPT_OZAKI_DIGITS, args.ozaki_digits)
+    ctx.set_option(g._lib.OPT_INT8_TILE, args.int8_tile)
     dist_train = world > 1 and args.train in ("auto", "distributed")
     D = None
     if dist_train:
@@ -412,20 +415,21 @@ def main():
                 src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (of measured; INT8 dense = 2 x bf16 dense nominally)"
             except Exception:
                 bf16, src = 1400.0, "2 x 1.4 PFLOP/s sustained bf16 (of fallback, B200_PROFILING.md)"
-            int8 = dict(kernel="oz::update_kernel<%d> (tcgen05.mma kind::i8, TMEM accumulators)" % S, digits=S,
+            kern = ("oz::update_kernel<%d>" if args.int8_tile == 64 else "oz::update128_kernel<%d>") % S
+            int8 = dict(kernel=kern + " (tcgen05.mma kind::i8, TMEM accumulators)", digits=S, tile=args.int8_tile,
                         int8_products_per_fp64_product=pairs,
                         achieved_int8_tops=(achieved * pairs) if achieved else None, peak_int8_tops=2 * bf16,
                         frac_of_int8_peak=(achieved * pairs / (2 * bf16)) if achieved else None, peak_source=src)
-            kname = ("oz::update_kernel<%d> (variance pass v = L^-1 K_star by blocked substitution with the O(n^2 m) "
+            kname = (kern + " (variance pass v = L^-1 K_star by blocked substitution with the O(n^2 m) "
                      "products as exact INT8 digit products on tcgen05 / TMEM; FP64 diagonal solves and column norms in "
-                     "gemm_kernel<TrsmLeftDiagPolicy>)" % S)
+                     "gemm_kernel<TrsmLeftDiagPolicy>)")
         roofline = dict(kernel=kname,
                         bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s",
                         frac=(achieved / peak_tf) if achieved else None, int8=int8, predict_path=used_path,
                         # one ncu --set full capture of a mid-sweep launch of this kernel (profiles/README.md):
                         # dram__bytes_read + write = 4.95e9 B for a launch whose algorithmic bytes (V rows read once,
                         # L row panel) are 3.8e9 B
-                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 and used_path != 4 else (1.1167e9 if used_path == 4 else None)),
+                        traffic=(4.946e9 if not timers["trtri"] and n == 50000 and used_path != 4 else (1.1167e9 if used_path == 4 and args.int8_tile == 64 else None)),
                         traffic_note=("dram bytes of ONE captured launch of oz::update_kernel<7> (ncu --set full, K = 16 256, "
                                       "9472 test points; algorithmic bytes of that launch 1.10e9), not per step; "
                                       "profiles/README.md") if used_path == 4 else

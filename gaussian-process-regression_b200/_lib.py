@@ -24,6 +24,7 @@ OPT_GRAM_DMMA = 1
 OPT_PREDICT_PATH = 2
 OPT_OZAKI_DIGITS = 3
 OPT_INT8_AUTO = 4
+OPT_INT8_TILE = 5
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 
 

@@ -65,6 +65,7 @@ struct gprc_ctx {
   int opt_predict_path = 0;
   int opt_ozaki_digits = 7;
   int opt_int8_auto = 1;
+  int opt_int8_tile = 64;
   int last_predict_path = 0;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};

@@ -354,6 +354,11 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     c->opt_predict_path = value;
     return 0;
   }
+  if (option == GPRC_OPT_INT8_TILE) {
+    GPRC_ARG(value == 64 || value == 128);
+    c->opt_int8_tile = value;
+    return 0;
+  }
   if (option == GPRC_OPT_INT8_AUTO) {
     c->opt_int8_auto = value ? 1 : 0;
     return 0;
@@ -731,8 +736,10 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   static bool configured[64] = {false};
   if (!configured[c->device & 63]) {
     GPRC_CUDA(cudaFuncSetAttribute(oz::update_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    GPRC_CUDA(cudaFuncSetAttribute(oz::update128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg2<S>::SMEM_BYTES));
     configured[c->device & 63] = true;
   }
+  const bool wide = c->opt_int8_tile == 128;  // 128 x 128 tiles, orders in two passes (ozaki.cuh, update128_kernel)
   GPRC_CHECK(oz_factor_digits<S>(c, F));
   const size_t need = (size_t)ws.mc * F.n_pad * S;
   if (ws.oz_bytes < need) {
@@ -753,13 +760,19 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   for (int i = 0; i < nt; ++i) {
     if (i > 0) {
       oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 0, nullptr};
-      oz::update_kernel<S, false><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
+      if (wide)
+        oz::update128_kernel<S><<<(unsigned)(mcur_pad / oz::BN2), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES, c->stream>>>(up);
+      else
+        oz::update_kernel<S, false><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
       c->launches++;
     }
     TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};
     GPRC_CHECK(launch_gemm(c, dg, dim3((unsigned)ntc)));
     if (i + 1 < nt) {
-      oz::split_v_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN), 4), 128, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
+      if (wide)
+        oz::split_v128_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN2), 4), 256, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
+      else
+        oz::split_v_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN), 4), 128, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
       c->launches++;
     }
   }

@@ -516,5 +516,248 @@ __global__ void __launch_bounds__(THREADS, 1) update_kernel(const UpdateParams p
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Wide variant: one CTA per 128 L-rows x 128 test points, the orders in TWO passes over the same k-range.
+//
+// A 128 x 64 x 32 MMA with both operands in shared memory takes 32 + 16 = 48 clk (4 KB of A + 2 KB of B through the
+// 128 B/clk operand port; its math takes 32), a 128 x 128 x 32 MMA takes 64 clk = its math floor (tools/oz_test rate).
+// 128 columns leave room for only 4 accumulators in the 512 TMEM columns, so the S orders are split:
+//   pass 0: orders [0, S-4)   needs digit planes 0 .. S-5 of both operands   (S = 7: 6 products per k-step, 24 KB)
+//   pass 1: orders [S-4, S)   needs all S planes                             (S = 7: 22 products per k-step, 56 KB)
+// Each pass runs over a drain interval of k and is drained (R -= ...) before the other starts.  The shared-memory ring
+// is re-partitioned per pass (small stages need a deeper ring to cover the feed latency); `pass_done` tells the
+// producer that every MMA of the previous pass has read its stages.
+// V digit tiles for this kernel are 128 points wide: Vs[128-point tile][k block][digit][128 x 32].
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BN2 = 128;
+constexpr int B2_TILE = BN2 * BK;  // 4096 B
+
+template <int S>
+struct Cfg2 {
+  static_assert(S >= 5 && S <= 8, "5..8 digits");
+  static constexpr int NLO = S - 4;                         // orders of pass 0
+  static constexpr int PAIRS0 = NLO * (NLO + 1) / 2;
+  static constexpr int PAIRS1 = S * (S + 1) / 2 - PAIRS0;
+  static constexpr int STAGE0 = NLO * (A_TILE + B2_TILE);   // pass 0 loads planes 0 .. NLO-1
+  static constexpr int STAGE1 = S * (A_TILE + B2_TILE);
+  static constexpr int RING = (215 * 1024) / STAGE1 * STAGE1;
+  static constexpr int STAGES1 = RING / STAGE1;
+  static constexpr int STAGES0 = (RING / STAGE0) > 8 ? 8 : (RING / STAGE0);
+  static constexpr int SMEM_BYTES = RING + DRAIN_STAGING_BYTES + 512;
+  static constexpr int KC = (S <= 7) ? 16384 : 8192;
+};
+
+// block row i of V -> 128-point digit tiles.  grid (mpad / 128, 4), 256 threads
+template <int S>
+__global__ void __launch_bounds__(256) split_v128_kernel(const double* __restrict__ T, long ldt, int i,
+                                                         const int* __restrict__ ecol, int8_t* __restrict__ Vs, int KB,
+                                                         int* __restrict__ error) {
+  const int tc = blockIdx.x, kq = blockIdx.y;
+  const int nn = threadIdx.x & 127, kh = threadIdx.x >> 7;
+  const long t = (long)tc * BN2 + nn;
+  const int e = ecol[t];
+  const double* p = T + t + ((long)i * BM + kq * BK + kh * 16) * ldt;
+  long long Y[16];
+  bool ovf = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) Y[j] = biased<S>(to_fixed<S>(p[(long)j * ldt], e, &ovf));
+  if (ovf) atomicOr(error, 2);
+  int8_t* tile = Vs + ((long)tc * KB + (4 * i + kq)) * (long)(S * B2_TILE) + tile_off(nn, kh * 16);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v |= (uint32_t)(digit<S>(Y[q * 4 + b], s) & 0xFF) << (8 * b);
+      w[q] = v;
+    }
+    *reinterpret_cast<uint4*>(tile + s * B2_TILE) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(THREADS, 1) update128_kernel(const UpdateParams p) {
+  using C = Cfg2<S>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stg_all = reinterpret_cast<double*>(smem_raw + C::RING);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::RING + DRAIN_STAGING_BYTES);  // 8 + 8: pass 0 / pass 1
+  uint64_t* empty = full + 16;
+  uint64_t* tmem_full = empty + 16;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint64_t* pass_done = tmem_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pass_done + 1);
+  static_assert(40 * 8 + 8 <= 512, "barrier block");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tc = blockIdx.x;
+  const int KT = 4 * p.i;
+  constexpr int KT_CHUNK = C::KC / BK;
+  const int nchunks = (KT + KT_CHUNK - 1) / KT_CHUNK;
+  // a "round" = (chunk, pass); round r = 2 * chunk + pass
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), 1);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    mbar_init(smem_u32(tmem_empty), 4);
+    mbar_init(smem_u32(pass_done), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    const int8_t* a_src = p.Ls + (long)p.i * p.KB * (long)(S * A_TILE);
+    const int8_t* b_src = p.Vs + (long)tc * p.KB * (long)(S * B2_TILE);
+    int cnt[2] = {0, 0};  // stages produced so far per pass: slot = n % ring size, use index (barrier phase) = n / ring size;
+                          // strictly round-robin across the rounds of a pass, mirrored by the consumer
+    for (int r = 0; r < 2 * nchunks; ++r) {
+      const int pass = r & 1, c = r >> 1;
+      const int kt0 = c * KT_CHUNK, kt1 = min(KT, kt0 + KT_CHUNK);
+      const int nst = pass ? C::STAGES1 : C::STAGES0, sbytes = pass ? C::STAGE1 : C::STAGE0;
+      const int planes = pass ? S : C::NLO;
+      // the ring is about to be re-partitioned: every MMA of the previous round must have read its stages
+      if (r > 0) mbar_wait_guarded(smem_u32(pass_done), (r - 1) & 1, p.error, 8);
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const int n = cnt[pass]++, s = n % nst;
+        // reuse of slot s inside this round: wait for the release of its previous use (same round only: across rounds
+        // pass_done already covers it, and the phase bookkeeping of `empty` continues per pass)
+        if (kt - kt0 >= nst) mbar_wait_guarded(smem_u32(empty + pass * 8 + s), ((n / nst) - 1) & 1, p.error, 16);
+        if (elect_one()) {
+          const uint32_t bar = smem_u32(full + pass * 8 + s);
+          const uint32_t dst = smem_u32(smem_raw + s * sbytes);
+          mbar_arrive_expect_tx(bar, (uint32_t)sbytes);
+          bulk_g2s(dst, a_src + (long)kt * (S * A_TILE), planes * A_TILE, bar);
+          bulk_g2s(dst + planes * A_TILE, b_src + (long)kt * (S * B2_TILE), planes * B2_TILE, bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc_i8(BM, BN2);
+      int cnt[2] = {0, 0};
+      for (int r = 0; r < 2 * nchunks; ++r) {
+        const int pass = r & 1, c = r >> 1;
+        const int kt0 = c * KT_CHUNK, kt1 = min(KT, kt0 + KT_CHUNK);
+        const int nst = pass ? C::STAGES1 : C::STAGES0, sbytes = pass ? C::STAGE1 : C::STAGE0;
+        if (r > 0) {  // accumulators of the previous round drained
+          mbar_wait_guarded(smem_u32(tmem_empty), (r - 1) & 1, p.error, 32);
+          tc_fence_after();
+        }
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int n = cnt[pass]++, s = n % nst;
+          mbar_wait_guarded(smem_u32(full + pass * 8 + s), (n / nst) & 1, p.error, 64);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem_raw + s * sbytes);
+          const bool first = (kt == kt0);
+          if (pass == 0) {
+            const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + C::NLO * A_TILE, 128, 256);
+#pragma unroll
+            for (int a = 0; a < C::NLO; ++a)
+#pragma unroll
+              for (int b = 0; b < C::NLO - a; ++b)
+                mma_i8(tmem_base + (uint32_t)((a + b) * BN2), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                       bd0 + (uint64_t)(b * (B2_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+          } else {
+            const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + S * A_TILE, 128, 256);
+#pragma unroll
+            for (int a = 0; a < S; ++a)
+#pragma unroll
+              for (int b = 0; b < S - a; ++b)
+                if (a + b >= C::NLO)  // first product into accumulator a + b - NLO of this round: a = 0
+                  mma_i8(tmem_base + (uint32_t)((a + b - C::NLO) * BN2), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                         bd0 + (uint64_t)(b * (B2_TILE >> 4)), idesc, (!first || a > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(empty + pass * 8 + s));
+        }
+        tc_commit(smem_u32(tmem_full));  // accumulators of this round complete
+        tc_commit(smem_u32(pass_done));  // ... and its stages have been read
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== drain =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const double sr = p.scale_row[(long)p.i * BM + row];
+    const double* sc = p.scale_col + (long)tc * BN2;
+    double* stg = stg_all + q * (32 * 9);
+    double* cbase = p.T + (long)tc * BN2 + ((long)p.i * BM + q * 32 + (lane >> 3)) * p.ldt + (lane & 7);
+    {
+      const double* prow = p.T + (long)tc * BN2 + ((long)p.i * BM + row) * p.ldt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) prefetch_l2(prow + j * 16);
+    }
+    constexpr int NHI = 4;
+    for (int r = 0; r < 2 * nchunks; ++r) {
+      const int pass = r & 1;
+      mbar_wait_guarded(smem_u32(tmem_full), r & 1, p.error, 128);
+      tc_fence_after();
+      // pass 0: sum_{o < NLO} acc_o 256^-o;  pass 1: 256^-NLO sum_{j < 4} acc_{NLO + j} 256^-j
+      const double srp = pass ? ldexp(sr, -8 * C::NLO) : sr;
+#pragma unroll 1
+      for (int g = 0; g < BN2 / 8; ++g) {
+        int32_t acc[NHI][8];
+        if (pass == 0) {
+#pragma unroll
+          for (int o = 0; o < C::NLO; ++o)
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN2 + g * 8), acc[o]);
+        } else {
+#pragma unroll
+          for (int o = 0; o < NHI; ++o)
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN2 + g * 8), acc[o]);
+        }
+        double cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = cbase[(long)(it * 4) * p.ldt + g * 8];
+        double scv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scv[j] = __ldg(sc + g * 8 + j);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double h;
+          if (pass == 0) {
+            h = (double)acc[C::NLO - 1][j];
+#pragma unroll
+            for (int o = C::NLO - 2; o >= 0; --o) h = fma(h, 0.00390625, (double)acc[o][j]);
+          } else {
+            h = (double)acc[NHI - 1][j];
+#pragma unroll
+            for (int o = NHI - 2; o >= 0; --o) h = fma(h, 0.00390625, (double)acc[o][j]);
+          }
+          stg[lane * 9 + j] = (srp * scv[j]) * h;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] -= stg[(it * 4 + (lane >> 3)) * 9 + (lane & 7)];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cbase[(long)(it * 4) * p.ldt + g * 8] = cur[it];
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace oz
 }  // namespace gprc

@@ -61,8 +61,11 @@ enum {
                                on the INT8 tensor cores (tcgen05, Ozaki digit splitting; FP64 diagonal solves) */
   GPRC_OPT_OZAKI_DIGITS = 3, /* 8-bit digits per operand entry on path 4: 6, 7 (default; 54 bits below the row /
                                column maximum) or 8 */
-  GPRC_OPT_INT8_AUTO = 4 /* 1 (default): the automatic choice takes path 4 where it takes the substitution today
+  GPRC_OPT_INT8_AUTO = 4, /* 1 (default): the automatic choice takes path 4 where it takes the substitution today
                             (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
+  GPRC_OPT_INT8_TILE = 5 /* test points per CTA on path 4: 64 (default: all orders in one pass, 7 accumulators in
+                            tensor memory) or 128 (128 x 128 x 32 MMAs at their math floor, orders in two passes; 1.4 x
+                            fewer tensor-pipe cycles but 1.4 x the HBM traffic -- equal under the 1000 W cap today) */
 
 };
 

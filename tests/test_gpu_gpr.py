@@ -185,8 +185,9 @@ def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
     assert_mean_var(got, ref, ok(Xs, Xs))
 
 
-@pytest.mark.parametrize("digits,tol", [(6, 1e-10), (7, 1e-12), (8, 1e-12)])
-def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tol):
+@pytest.mark.parametrize("digits,tile,tol", [(6, 64, 1e-10), (7, 64, 1e-12), (8, 64, 1e-12), (7, 128, 1e-12), (6, 128, 1e-10),
+                                             (8, 128, 1e-12)])
+def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tile, tol):
     """Path 4 against path 2 on the same factor: 1500 training points (12 block rows), polynomial kernel (k** varies
     per test point, so the per-point exponents differ), more than one 64-point tile per SM."""
     rng = np.random.default_rng(35)
@@ -200,11 +201,13 @@ def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tol):
     for path in (2, 4):
         ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
         ctx.set_option(gprc._lib.OPT_OZAKI_DIGITS, digits)
+        ctx.set_option(gprc._lib.OPT_INT8_TILE, tile)
         try:
             out[path] = g.predict(Xs)
         finally:
             ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
             ctx.set_option(gprc._lib.OPT_OZAKI_DIGITS, 7)
+            ctx.set_option(gprc._lib.OPT_INT8_TILE, 64)
     kss = (np.sum(Xs * Xs, axis=0) + 1.0) ** 3
     np.testing.assert_allclose(out[2][:, 0], out[4][:, 0], rtol=1e-13, atol=0)  # the mean does not go through the variance pass
     assert np.max(np.abs(out[2][:, 1] - out[4][:, 1]) / kss) < tol

@@ -36,7 +36,7 @@ __global__ void clock_probe(long long* out) {
   out[1] = (long long)(t1 - t0);
 }
 
-template <int S, bool TS>
+template <int S, bool TS, bool WIDE = false>
 static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, int dbg) {
   const long n_pad = n, KB = n_pad / 32;
   std::mt19937_64 rng(12345);
@@ -72,14 +72,26 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   oz::rowmax_kernel<<<nt, 256>>>(dL, n_pad, derow, dsr);
   oz::split_l_kernel<S><<<dim3(4 * nt, nt), 256>>>(dL, n_pad, derow, dLs, (int)KB, derr);
   oz::colscale_kernel<<<(unsigned)((mc + 255) / 256), 256>>>(dkss, mc, mc, decol, dsc);
-  for (int b = 0; b < i; ++b)
-    oz::split_v_kernel<S><<<dim3((unsigned)(mc / 64), 4), 128>>>(dT, mc, b, decol, dVs, (int)KB, derr);
+  for (int b = 0; b < i; ++b) {
+    if constexpr (WIDE) oz::split_v128_kernel<S><<<dim3((unsigned)(mc / 128), 4), 256>>>(dT, mc, b, decol, dVs, (int)KB, derr);
+    else oz::split_v_kernel<S><<<dim3((unsigned)(mc / 64), 4), 128>>>(dT, mc, b, decol, dVs, (int)KB, derr);
+  }
   CK(cudaDeviceSynchronize());
   int herr = 0;
   CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
   printf("split done, overflow flag = %d\n", herr);
 
-  CK(cudaFuncSetAttribute(oz::update_kernel<S, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+  auto launch = [&](const oz::UpdateParams& q) {
+    if constexpr (WIDE) oz::update128_kernel<S><<<(unsigned)(mc / 128), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES>>>(q);
+    else oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(q);
+  };
+  if constexpr (WIDE) {
+    CK(cudaFuncSetAttribute(oz::update128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg2<S>::SMEM_BYTES));
+    printf("wide kernel: 128 x 128 tiles, two order passes, ring %d B, stages %d / %d\n", oz::Cfg2<S>::RING,
+           oz::Cfg2<S>::STAGES0, oz::Cfg2<S>::STAGES1);
+  } else {
+    CK(cudaFuncSetAttribute(oz::update_kernel<S, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+  }
   long long* dtrace = nullptr;
   CK(cudaMalloc(&dtrace, 512 * 4 * 8));
   CK(cudaMemset(dtrace, 0, 512 * 4 * 8));
@@ -91,11 +103,11 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    for (int w = 0; w < 100; ++w) oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+    for (int w = 0; w < 100; ++w) launch(p);
     CK(cudaDeviceSynchronize());
     const int reps = 20;
     cudaEventRecord(a);
-    for (int w = 0; w < reps; ++w) oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+    for (int w = 0; w < reps; ++w) launch(p);
     cudaEventRecord(b);
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -103,7 +115,7 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     ms /= reps;
     if (dbg & 32) {
       p.trace = dtrace;
-      oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+      launch(p);
       CK(cudaDeviceSynchronize());
       std::vector<long long> tr(512 * 4);
       CK(cudaMemcpy(tr.data(), dtrace, 512 * 4 * 8, cudaMemcpyDeviceToHost));
@@ -120,13 +132,13 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     long long hclk[2];
     CK(cudaMemcpy(hclk, dclk, 16, cudaMemcpyDeviceToHost));
     const double mhz = (double)hclk[0] / (double)hclk[1] * 1e3;
-    printf("update_kernel<%d,%s> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
-           "%.0f clk per k-step\n", S, TS ? "TS" : "SS", dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
-           ms * 1e-3 * mhz * 1e6 / (4.0 * i) / ((mc / 64 + 147) / 148));
+    printf("update_kernel<%d,%s%s> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
+           "%.0f clk per k-step\n", S, TS ? "TS" : "SS", WIDE ? " wide" : "", dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
+           ms * 1e-3 * mhz * 1e6 / (4.0 * i) / ((mc / (WIDE ? 128 : 64) + 147) / 148));
     return 0;
   }
 
-  oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(p);
+  launch(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("update kernel failed: %s\n", cudaGetErrorString(e));
@@ -193,8 +205,8 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
       }
     }
   }
-  printf("RESULT S=%d %s i=%d: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
-         S, TS ? "TS" : "SS", i, herr, max_emul, bad, 128 * mc, max_fp64, max_ref, bad == 0 ? "  OK" : "  FAIL");
+  printf("RESULT S=%d %s%s i=%d: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
+         S, TS ? "TS" : "SS", WIDE ? " wide" : "", i, herr, max_emul, bad, 128 * mc, max_fp64, max_ref, bad == 0 ? "  OK" : "  FAIL");
   return bad == 0 ? 0 : 1;
 }
 
@@ -219,11 +231,22 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int count, int rot, in
     const uint32_t idesc = oz::instr_desc_i8(128, N);
     const uint32_t s0 = smem_u32(sm);
     const long long t0 = clock64();
-    for (int it = 0; it < count; ++it) {
-      const int r = it % rot, q = it % nsrc;
-      const uint64_t ad = oz::smem_desc(s0 + q * 4096, 128, 256), bd = oz::smem_desc(s0 + 65536 + q * (N * 32), 128, 256);
-      if (TS) oz::mma_i8_ts(tb + r * N, tb + 448 + (q % 8) * 8, bd, idesc, 1u);
-      else oz::mma_i8(tb + r * N, ad, bd, idesc, 1u);
+    // 8 products per trip, descriptors and accumulator addresses precomputed: the loop must not be issue-bound
+    uint64_t ad[8], bd[8];
+    uint32_t dd[8], at[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      ad[u] = oz::smem_desc(s0 + (u % nsrc) * 4096, 128, 256);
+      bd[u] = oz::smem_desc(s0 + 65536 + (u % nsrc) * (N * 32), 128, 256);
+      dd[u] = tb + (u % rot) * N;
+      at[u] = tb + 448 + (u % nsrc) * 8;
+    }
+    for (int it = 0; it < count; it += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (TS) oz::mma_i8_ts(dd[u], at[u], bd[u], idesc, 1u);
+        else oz::mma_i8(dd[u], ad[u], bd[u], idesc, 1u);
+      }
     }
     oz::tc_commit(smem_u32(&bar));
     oz::mbar_wait_guarded(smem_u32(&bar), 0, (int*)out + 8, 1);
@@ -293,15 +316,16 @@ int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "digits")
     return digits_selftest<6>() | digits_selftest<7>() | digits_selftest<8>() | digits_selftest<1>() | digits_selftest<2>();
   if (argc >= 2 && std::string(argv[1]) == "rate") {
+    mma_rate<32, false>(1, 1);
     mma_rate<64, false>(1, 1);
-    mma_rate<64, false>(7, 1);
     mma_rate<64, false>(7, 7);
-    mma_rate<64, true>(1, 1);
     mma_rate<64, true>(7, 7);
+    mma_rate<80, false>(6, 6);
+    mma_rate<96, false>(4, 7);
     mma_rate<128, false>(1, 1);
     mma_rate<128, false>(3, 7);
     mma_rate<128, true>(3, 7);
-    mma_rate<256, false>(1, 1);
+    mma_rate<192, false>(2, 7);
     mma_rate<256, false>(1, 7);
     mma_rate<256, true>(1, 7);
     return 0;
@@ -316,16 +340,18 @@ int main(int argc, char** argv) {
   const int i = atoi(argv[5]);
   const uint32_t lbo = argc > 7 ? (uint32_t)atoi(argv[6]) : 0u, sbo = 0u;  // argv[6] = 1 selects the TS kernel
   const int dbg = argc > 8 ? atoi(argv[8]) : 0;
-  if (n % 128 || mc % 64 || i < 1 || i >= n / 128) {
+  if (n % 128 || mc % 128 || i < 1 || i >= n / 128) {
     printf("bad sizes\n");
     return 64;
   }
   switch (S) {
     case 1: return (lbo == 1 ? run<1, true>(timing, n, mc, i, lbo, sbo, dbg) : run<1, false>(timing, n, mc, i, lbo, sbo, dbg));
     case 2: return (lbo == 1 ? run<2, true>(timing, n, mc, i, lbo, sbo, dbg) : run<2, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 6: return (lbo == 1 ? run<6, true>(timing, n, mc, i, lbo, sbo, dbg) : run<6, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 7: return (lbo == 1 ? run<7, true>(timing, n, mc, i, lbo, sbo, dbg) : run<7, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 8: return run<8, false>(timing, n, mc, i, lbo, sbo, dbg);
+    case 6: return (lbo == 2 ? run<6, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                             : lbo == 1 ? run<6, true>(timing, n, mc, i, lbo, sbo, dbg) : run<6, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 7: return (lbo == 2 ? run<7, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                             : lbo == 1 ? run<7, true>(timing, n, mc, i, lbo, sbo, dbg) : run<7, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 8: return (lbo == 2 ? run<8, false, true>(timing, n, mc, i, lbo, sbo, dbg) : run<8, false>(timing, n, mc, i, lbo, sbo, dbg));
   }
   printf("S must be 1, 2, 6, 7 or 8\n");
   return 64;
