@@ -23,11 +23,19 @@
 .gprc_formals <- function(name)
   setdiff(names(formals(get(paste0(name, ".matrix"), envir = asNamespace("gprc")))), c("x", "y"))
 
+# options(gprc.fit_engine = "library"): the same optimiser trajectories, run inside libgprc (gprc_fit_family: Brent_fmin,
+# vmmin and optim_until_error restated in C++, X and y uploaded once); default "R": optim() drives, one .Call per
+# evaluation.  Both give the same par / value.
 #' @export
 fit <- function(X, y, noise, cov_names = as.list(cov_df$name)) {
   if (!is.matrix(X)) dim(X) <- c(1, length(X))
   storage.mode(X) <- "double"
+  in_library <- identical(getOption("gprc.fit_engine", "R"), "library")
   results <- lapply(cov_names, function(cov) {
+    if (in_library) {
+      r <- .Call(C_gprc_fit_family, .gprc_ids[[cov]], X, as.double(y), as.double(noise), TRUE)
+      return(list(par = r[-1], value = r[1]))
+    }
     start <- cov_df[cov, ]$start[[1]]
     dens <- .dens_device(X, y, noise, cov)
     if (cov == "polynomial") {                       # degrees 1..10, Brent over sigma in [0, 5]

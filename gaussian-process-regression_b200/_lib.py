@@ -40,6 +40,8 @@ class GprcError(RuntimeError):
 # every symbol include/gprc.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _K = C.POINTER(GprcKernel)
+# gprc_objective_fn / gprc_gradient_fn: int (*)(const double* par, int npar, void* user, double* out)
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_int, c_double_p, C.c_int, C.c_void_p, c_double_p)
 SIGNATURES = {
     "gprc_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int]),
     "gprc_ctx_free": (None, [_P]),
@@ -79,6 +81,13 @@ SIGNATURES = {
                                   C.c_int, c_long_p]),
     "gprc_logml_batch": (C.c_int, [_P, _K, C.c_int, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double,
                                    c_double_p, c_double_p, c_long_p]),
+    "gprc_optim_brent": (C.c_int, [OBJECTIVE_FN, _P, C.c_double, C.c_double, C.c_double, c_double_p]),
+    "gprc_optim_vmmin": (C.c_int, [OBJECTIVE_FN, OBJECTIVE_FN, _P, c_double_p, C.c_int, C.c_int, C.c_double,
+                                   C.c_double, c_double_p, c_int_p, c_int_p]),
+    "gprc_optim_until_error": (C.c_int, [OBJECTIVE_FN, OBJECTIVE_FN, _P, c_double_p, C.c_int, C.c_int, C.c_double,
+                                         C.c_double, c_double_p, c_double_p]),
+    "gprc_fit_family": (C.c_int, [_P, C.c_int, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double, C.c_int,
+                                  c_double_p, c_int_p, c_double_p, c_long_p]),
     "gprc_gpc_fit": (C.c_int, [_P, _K, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double, C.c_int, C.c_int,
                                C.POINTER(_P), c_int_p, c_double_p, C.c_int, c_double_p, c_double_p, c_int_p]),
     "gprc_gpc_fit_precomputed": (C.c_int, [_P, c_double_p, C.c_long, c_double_p, C.c_double, C.c_int, C.c_int,

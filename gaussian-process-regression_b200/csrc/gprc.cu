@@ -11,6 +11,7 @@
 #include "gpc.cuh"
 #include "quad.cuh"
 #include "ozaki.cuh"
+#include "optim.hpp"
 
 namespace gprc {
 thread_local std::string g_last_error;
@@ -1383,8 +1384,9 @@ __global__ void sum_partials_kernel(const double* __restrict__ partial, int n, d
 }
 }  // namespace gprc
 
-extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
-                               double noise, int formula, double* grad, int nparam, long* info) {
+static int logml_grad_impl(gprc_ctx* c, const gprc_kernel* k, const double* X, bool x_on_device, int d, long n,
+                           const double* y, bool y_on_device, double noise, int formula, double* grad, int nparam,
+                           long* info) {
   GPRC_ARG(c && k && X && y && grad && info && n > 0 && d > 0);
   GPRC_ARG(k->id == GPRC_SQREXP || k->id == GPRC_GAMMAEXP || k->id == GPRC_RATQUAD || k->id == GPRC_POLYNOMIAL);
   const int np_expected = (k->id == GPRC_SQREXP) ? 1 : 2;
@@ -1399,8 +1401,8 @@ extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* 
   }
   // as coded the reference inverts the NOISE-FREE K (R/fit.R:136); the textbook formula uses K + noise I
   gprc_gpr* g = nullptr;
-  GPRC_CHECK(gpr_fit_common(c, k, X, false, d, n, y, false, nullptr, textbook ? noise : 0.0, &g, nullptr, info,
-                            nullptr));
+  GPRC_CHECK(gpr_fit_common(c, k, X, x_on_device, d, n, y, y_on_device, nullptr, textbook ? noise : 0.0, &g, nullptr,
+                            info, nullptr));
   if (*info != 0 || !g) return 0;
   DeviceGuard guard(c);
   FactorState& F = g->F;
@@ -1457,6 +1459,179 @@ extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* 
   dfree(Z);
   gprc_gpr_free(g);
   return rc;
+}
+
+extern "C" int gprc_logml_grad(gprc_ctx* c, const gprc_kernel* k, const double* X, int d, long n, const double* y,
+                               double noise, int formula, double* grad, int nparam, long* info) {
+  return logml_grad_impl(c, k, X, false, d, n, y, false, noise, formula, grad, nparam, info);
+}
+
+// =================================================================================================================
+// fit(): the optimiser inside the library (optim.hpp), R/fit.R:47-69, 113-162
+// =================================================================================================================
+extern "C" int gprc_optim_brent(gprc_objective_fn fn, void* user, double lower, double upper, double tol, double* xmin) {
+  GPRC_ARG(fn && xmin);
+  try {
+    *xmin = optim::brent_fmin(
+        [&](double x) {
+          double v = 0.0;
+          if (fn(&x, 1, user, &v) != 0) throw optim::ObjectiveError{};
+          return v;
+        },
+        lower, upper, tol);
+  } catch (const optim::ObjectiveError&) {
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int gprc_optim_vmmin(gprc_objective_fn fn, gprc_gradient_fn gr, void* user, double* par, int npar, int maxit,
+                                double abstol, double reltol, double* value, int* counts, int* fail) {
+  GPRC_ARG(fn && gr && par && npar > 0 && value);
+  try {
+    optim::VmminResult r = optim::vmmin(
+        par, npar,
+        [&](const double* p) {
+          double v = 0.0;
+          if (fn(p, npar, user, &v) != 0) throw optim::ObjectiveError{};
+          return v;
+        },
+        [&](const double* p, double* g) {
+          if (gr(p, npar, user, g) != 0) throw optim::ObjectiveError{};
+        },
+        maxit, abstol, reltol);
+    *value = r.value;
+    if (counts) {
+      counts[0] = r.fncount;
+      counts[1] = r.grcount;
+    }
+    if (fail) *fail = r.fail;
+  } catch (const optim::ObjectiveError&) {
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int gprc_optim_until_error(gprc_objective_fn fn, gprc_gradient_fn gr, void* user, const double* start,
+                                      int npar, int method, double lower, double upper, double* par, double* value) {
+  GPRC_ARG(fn && start && par && value && npar > 0 && (method == 0 || (method == 1 && gr)));
+  GPRC_ARG(method == 1 || npar == 1);
+  optim::FnN f = [&](const double* p) {
+    double v = 0.0;
+    if (fn(p, npar, user, &v) != 0) throw optim::ObjectiveError{};
+    return v;
+  };
+  optim::GrN g = [&](const double* p, double* out) {
+    if (gr(p, npar, user, out) != 0) throw optim::ObjectiveError{};
+  };
+  optim::UntilErrorResult r =
+      optim::optim_until_error(std::vector<double>(start, start + npar), f, method == 1 ? &g : nullptr, method == 0,
+                               lower, upper);
+  for (int i = 0; i < npar; ++i) par[i] = r.par[i];
+  *value = r.value;
+  return 0;
+}
+
+namespace {
+// the reference passes the optimiser's vector positionally: do.call(func, append(list(x, y), v)), R/fit.R:118
+gprc_kernel family_spec(int id, const double* v) {
+  gprc_kernel k{};
+  k.id = id;
+  switch (id) {
+    case GPRC_CONSTANT: k.c = v[0]; break;
+    case GPRC_LINEAR: k.sigma = v[0]; break;
+    case GPRC_POLYNOMIAL: k.sigma = v[0]; k.p = v[1]; break;
+    case GPRC_SQREXP: k.l = v[0]; break;
+    case GPRC_GAMMAEXP: k.l = v[0]; k.gamma = v[1]; break;
+    case GPRC_RATQUAD: k.l = v[0]; k.alpha = v[1]; break;
+  }
+  return k;
+}
+}  // namespace
+
+extern "C" int gprc_fit_family(gprc_ctx* c, int kernel_id, const double* X, int d, long n, const double* y,
+                               double noise, int minors_rule, double* par, int* npar, double* value,
+                               long* evaluations) {
+  GPRC_ARG(c && X && y && par && npar && value && n > 0 && d > 0);
+  GPRC_ARG(kernel_id >= GPRC_CONSTANT && kernel_id <= GPRC_RATQUAD);
+  DeviceGuard guard(c);
+  double *dX = nullptr, *dy = nullptr;
+  GPRC_CHECK(dmalloc(&dX, (size_t)d * n));
+  int rc = dmalloc(&dy, (size_t)n);
+  if (rc) {
+    dfree(dX);
+    return rc;
+  }
+  cudaMemcpyAsync(dX, X, sizeof(double) * d * n, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+  long n_fn = 0, n_gr = 0;
+  int hard_error = 0;  // a CUDA / argument error inside an evaluation: abort the search and report it
+  const double log_denorm_min = std::log(std::numeric_limits<double>::denorm_min());
+  // dens, R/fit.R:117-124
+  auto dens = [&](const double* v) -> double {
+    gprc_kernel k = family_spec(kernel_id, v);
+    gprc_gpr* g = nullptr;
+    double lp = 0.0, ml = 0.0;
+    long inf = 0;
+    ++n_fn;
+    const int r = gpr_fit_common(c, &k, dX, true, d, n, dy, true, nullptr, noise, &g, &lp, &inf, &ml);
+    if (g) gprc_gpr_free(g);
+    if (r != 0) {
+      hard_error = r;
+      throw optim::ObjectiveError{};
+    }
+    if (inf != 0 || !std::isfinite(lp)) throw optim::ObjectiveError{};             // chol() failed
+    if (minors_rule == 0 && !(ml >= log_denorm_min)) throw optim::ObjectiveError{};  // fit.R:119 with det underflow (A.4)
+    return lp;
+  };
+  const int nparam = (kernel_id == GPRC_GAMMAEXP || kernel_id == GPRC_RATQUAD || kernel_id == GPRC_POLYNOMIAL) ? 2 : 1;
+  // dens_deriv as coded, R/fit.R:126-139
+  optim::GrN deriv = [&](const double* v, double* gout) {
+    gprc_kernel k = family_spec(kernel_id, v);
+    long inf = 0;
+    ++n_gr;
+    const int r = logml_grad_impl(c, &k, dX, true, d, n, dy, true, noise, GPRC_GRAD_AS_CODED, gout, nparam, &inf);
+    if (r != 0) {
+      hard_error = r;
+      throw optim::ObjectiveError{};
+    }
+    if (inf != 0) throw optim::ObjectiveError{};  // solve(K): computationally singular
+  };
+  optim::UntilErrorResult best;
+  if (kernel_id == GPRC_POLYNOMIAL) {
+    // R/fit.R:145-156: Brent over sigma in [0, 5] for every degree 1..10, then which.max
+    bool have = false;
+    int best_deg = 1;
+    for (int deg = 1; deg <= 10 && !hard_error; ++deg) {
+      optim::FnN f = [&](const double* sig) {
+        const double v[2] = {sig[0], (double)deg};
+        return dens(v);
+      };
+      optim::UntilErrorResult r = optim::optim_until_error({1.0}, f, nullptr, true, 0.0, 5.0);
+      if (!have || r.value > best.value) {
+        best = r;
+        best_deg = deg;
+        have = true;
+      }
+    }
+    best.par = {best.par[0], (double)best_deg};
+  } else if (nparam == 1) {
+    best = optim::optim_until_error({1.0}, dens, nullptr, true, 0.0, 10.0);
+  } else {
+    best = optim::optim_until_error({1.0, 1.0}, dens, &deriv, false, 0.0, 0.0);
+  }
+  cudaStreamSynchronize(c->stream);
+  dfree(dX);
+  dfree(dy);
+  if (hard_error) return hard_error;
+  *npar = (int)best.par.size();
+  for (size_t i = 0; i < best.par.size(); ++i) par[i] = best.par[i];
+  *value = best.value;
+  if (evaluations) {
+    evaluations[0] = n_fn;
+    evaluations[1] = n_gr;
+  }
+  return 0;
 }
 
 // =================================================================================================================

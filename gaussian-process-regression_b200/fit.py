@@ -71,6 +71,18 @@ class Objective:
             raise OptimError("system is computationally singular")  # solve(K) of R/fit.R:136
         return grad
 
+    def fit_family(self, name):
+        """One pass of the loop body of R/fit.R:113-162 inside the library (gprc_fit_family, csrc/optim.hpp): X and y
+        are uploaded once, the optimiser (Brent_fmin / vmmin / optim_until_error restated in C++) runs in the call and
+        every dens / dens_deriv evaluation stays on the device.  Same trajectory as ``_fit_one`` on the host."""
+        par, npar, value = np.zeros(2), C.c_int(0), C.c_double(0.0)
+        evals = (C.c_long * 2)()
+        _lib.check(self.ctx.lib.gprc_fit_family(self.ctx.handle, _lib.KERNEL_IDS[name], _lib.dptr(self.xp),
+                                                self.X.shape[0], self.X.shape[1], _lib.dptr(self.y), self.noise,
+                                                0 if self.minors == "literal" else 1, _lib.dptr(par), C.byref(npar),
+                                                C.byref(value), evals))
+        return dict(par=par[:npar.value].copy(), value=value.value, evaluations=(evals[0], evals[1]))
+
     def dens_batch(self, name, thetas):
         """Independent evaluations in one call (multi-start / grid): returns logp (nan where not PD)."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
@@ -117,8 +129,12 @@ def optim_until_error(start, f, **kw):
         return dict(par=record[best][0], value=record[best][1])
 
 
-def _fit_one(obj, cov):
-    """One pass of the loop body of R/fit.R:113-162 for the covariance family ``cov``."""
+def _fit_one(obj, cov, engine="host"):
+    """One pass of the loop body of R/fit.R:113-162 for the covariance family ``cov``.  engine = "library" runs the
+    optimiser inside libgprc (Objective.fit_family); "host" drives it from here, one ABI call per evaluation."""
+    if engine == "library":
+        r = obj.fit_family(cov)
+        return dict(par=r["par"], value=r["value"])
     nparam = len(cov_dict[cov]["start"])
     f = lambda v: obj.dens(cov, v)
     kw = {}
@@ -137,7 +153,7 @@ def _fit_one(obj, cov):
     return optim_until_error(cov_dict[cov]["start"], f, **kw)
 
 
-def fit(X, y, noise, cov_names=None, ctx=None, minors="literal", group=None, verbose=True):
+def fit(X, y, noise, cov_names=None, ctx=None, minors="literal", group=None, verbose=True, engine="host"):
     """fit(X, y, noise, cov_names), R/fit.R:110-169 -> dict(par, cov, score, func).
 
     ``group``: optional torch.distributed process group; the covariance families are dealt round-robin to the ranks
@@ -148,11 +164,11 @@ def fit(X, y, noise, cov_names=None, ctx=None, minors="literal", group=None, ver
             raise KeyError(c)
     obj = Objective(X, y, noise, ctx=ctx, minors=minors)
     if group is None:
-        results = [_fit_one(obj, cov) for cov in cov_names]
+        results = [_fit_one(obj, cov, engine) for cov in cov_names]
     else:
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        mine = {i: _fit_one(obj, cov) for i, cov in enumerate(cov_names) if i % world == rank}
+        mine = {i: _fit_one(obj, cov, engine) for i, cov in enumerate(cov_names) if i % world == rank}
         payload = {i: (np.atleast_1d(r["par"]).tolist(), float(r["value"])) for i, r in mine.items()}
         gathered = [None] * world
         dist.all_gather_object(gathered, payload, group=group)

@@ -226,6 +226,25 @@ SEXP C_gprc_gpc_get(SEXP ptr, SEXP what) {
   return out;
 }
 
+/* one pass of fit()'s loop body inside the library (gprc_fit_family, R/fit.R:113-162): c(value, par...) */
+SEXP C_gprc_fit_family(SEXP id, SEXP X, SEXP y, SEXP noise, SEXP strict) {
+  double par[2] = {0.0, 0.0}, value = NA_REAL; int npar = 0;
+  int rc = gprc_fit_family(ctx(), Rf_asInteger(id), REAL(X), Rf_nrows(X), XLENGTH(y), REAL(y), Rf_asReal(noise),
+                           Rf_asLogical(strict) ? 0 : 1, par, &npar, &value, NULL);
+  if (rc) Rf_error("gprc: %s", gprc_last_error());
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 1 + npar));
+  REAL(out)[0] = value;
+  for (int i = 0; i < npar; ++i) REAL(out)[1 + i] = par[i];
+  UNPROTECT(1);
+  return out;
+}
+
+/* gprc_ctx_set_option(option, value): predict path, INT8 digits / tile, ... (include/gprc.h GPRC_OPT_*) */
+SEXP C_gprc_set_option(SEXP option, SEXP value) {
+  if (gprc_ctx_set_option(ctx(), Rf_asInteger(option), Rf_asInteger(value)) != 0) Rf_error("gprc: %s", gprc_last_error());
+  return R_NilValue;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"C_gprc_cov_matrix", (DL_FUNC)&C_gprc_cov_matrix, 3},
     {"C_gprc_gpr_fit", (DL_FUNC)&C_gprc_gpr_fit, 5},
@@ -234,6 +253,8 @@ static const R_CallMethodDef call_methods[] = {
     {"C_gprc_gpr_get", (DL_FUNC)&C_gprc_gpr_get, 2},
     {"C_gprc_logml", (DL_FUNC)&C_gprc_logml, 4},
     {"C_gprc_logml_grad", (DL_FUNC)&C_gprc_logml_grad, 6},
+    {"C_gprc_fit_family", (DL_FUNC)&C_gprc_fit_family, 5},
+    {"C_gprc_set_option", (DL_FUNC)&C_gprc_set_option, 2},
     {"C_gprc_gpc_fit", (DL_FUNC)&C_gprc_gpc_fit, 6},
     {"C_gprc_gpc_predict_latent", (DL_FUNC)&C_gprc_gpc_predict_latent, 4},
     {"C_gprc_gpc_predict_class", (DL_FUNC)&C_gprc_gpc_predict_class, 2},

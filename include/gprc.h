@@ -163,6 +163,32 @@ int gprc_logml_grad(gprc_ctx* ctx, const gprc_kernel* k, const double* X, int d,
 int gprc_logml_batch(gprc_ctx* ctx, const gprc_kernel* specs, int nspec, const double* X, int d, long n,
                      const double* y, double noise, double* logp, double* min_leading_logdet, long* info);
 
+/* ---- fit(): the optimiser inside the library -- R/fit.R:47-69, 143-160 --------------------- */
+/* Objective / gradient callbacks: return 0 and the value(s), or non-zero when the evaluation fails (the reference's
+ * objective throws: stopifnot, chol, solve).  `par` has `npar` entries. */
+typedef int (*gprc_objective_fn)(const double* par, int npar, void* user, double* value);
+typedef int (*gprc_gradient_fn)(const double* par, int npar, void* user, double* grad);
+/* R's Brent_fmin (src/appl/fmin.c: optimize(), optim(method = "Brent")): minimiser of fn on [lower, upper].
+ * Returns 1 if fn failed (no R counterpart: the error would propagate), else 0. */
+int gprc_optim_brent(gprc_objective_fn fn, void* user, double lower, double upper, double tol, double* xmin);
+/* R's vmmin (src/appl/optim.c: optim(method = "BFGS")); par: start -> minimiser.  counts = {fn, gr} evaluations;
+ * fail = 1 when maxit was reached.  Returns 1 if the start value is not finite or a callback failed. */
+int gprc_optim_vmmin(gprc_objective_fn fn, gprc_gradient_fn gr, void* user, double* par, int npar, int maxit,
+                     double abstol, double reltol, double* value, int* counts, int* fail);
+/* optim_until_error(start, f, method, ...) with control = list(fnscale = -1) (R/fit.R:47-69,149-150,158): MAXIMISES
+ * fn; a failing objective scores -10000; a failing gradient ends the search and the best recorded evaluation wins.
+ * method: 0 = Brent on [lower, upper] (npar = 1), 1 = BFGS from `start` (gr required). */
+int gprc_optim_until_error(gprc_objective_fn fn, gprc_gradient_fn gr, void* user, const double* start, int npar,
+                           int method, double lower, double upper, double* par, double* value);
+/* One pass of fit()'s loop body (R/fit.R:113-162) for the covariance family `kernel_id`, entirely inside the library:
+ * X (d x n) and y are uploaded once and every dens / dens_deriv evaluation of the trajectory runs on the device
+ * (the trajectory is the one fit.py's host optimiser produces through gprc_logml / gprc_logml_grad).
+ * minors_rule: 0 = literal R/fit.R:119 (det underflow), 1 = Cholesky succeeds.  par (2), npar, value =
+ * the family's optimum (polynomial: (sigma, degree) over degrees 1..10, R/fit.R:145-156).  evaluations (nullable, 2) =
+ * {objective, gradient} device evaluations. */
+int gprc_fit_family(gprc_ctx* ctx, int kernel_id, const double* X, int d, long n, const double* y, double noise,
+                    int minors_rule, double* par, int* npar, double* value, long* evaluations);
+
 /* ---- (4) GPC: Laplace-approximation Newton loop -- GPC$initialize, R/GPCclass.R:73-103 ------------------ */
 /* guard != 0 applies the reference's divergence rule R/GPCclass.R:90 literally; when it fires
  * the return value is 0, *status = 1 and no model is created.  objective_trace receives min(iters, trace_cap)

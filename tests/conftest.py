@@ -10,6 +10,20 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_next: needs a CUDA device; written after the round's GPU budget was spent and "
+                                       "not yet run on a B200 -- run with -m gpu_next and promote to `gpu` once green")
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m "not gpu"` (the CPU tier) also selects gpu_next tests: they need a device, so they are skipped without one
+    import shutil
+    has_gpu = shutil.which("nvidia-smi") is not None and os.system("nvidia-smi -L > /dev/null 2>&1") == 0
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="gpu_next: needs a CUDA device")
+    for item in items:
+        if "gpu_next" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -163,7 +163,7 @@ def _worker(rank, world, port, q):
         def __init__(self, *a, **k):
             pass
 
-    def fake_fit_one(obj, cov):
+    def fake_fit_one(obj, cov, engine="host"):
         seen.append(cov)
         score = {"sqrexp": -3.0, "gammaexp": -2.5, "constant": -9.0, "linear": -1.0, "polynomial": -4.0,
                  "rationalquadratic": -2.0}[cov]
