@@ -72,6 +72,8 @@ SIGNATURES = {
     "gprc_gpr_predict_dev": (C.c_int, [_P, _P, C.c_long, _P, _P]),
     "gprc_gpr_predict_precomputed": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, c_double_p]),
     "gprc_gpr_predict_cov": (C.c_int, [_P, c_double_p, C.c_long, c_double_p, c_double_p]),
+    "gprc_grid_points": (C.c_int, [_P, c_double_p, C.c_int, C.c_int, c_double_p]),
+    "gprc_gpr_predict_grid": (C.c_int, [_P, c_double_p, C.c_int, c_double_p, c_double_p]),
     "gprc_gpr_get": (C.c_int, [_P, C.c_int, c_double_p]),
     "gprc_gpr_n": (C.c_long, [_P]),
     "gprc_gpr_free": (None, [_P]),

@@ -1104,6 +1104,95 @@ extern "C" int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, doub
   return predict_pointwise_dev(g->ctx, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar);
 }
 
+// ---- test grids on the device: combine_all(lapply(1:D, seq(lo, hi, length.out = per_dim))) ------------
+namespace gprc {
+// out: d x m (points contiguous), m = per_dim^d; the FIRST dimension varies slowest, the last fastest
+// (R/simulation.R:338-349: row k = rep(rep(lst[[k]], each = prod(lengths after k)), times = prod(lengths before k))).
+// seq(lo, hi, length.out = n) as numpy.linspace evaluates it: lo + i * ((hi - lo) / (n - 1)), last point = hi exactly.
+__global__ void __launch_bounds__(256) grid_points_kernel(const double* __restrict__ limits /* d x 2: lo, hi */, int d,
+                                                          int per_dim, long m, double* __restrict__ out) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  long rest = j;
+  for (int k = d - 1; k >= 0; --k) {
+    const int i = (int)(rest % per_dim);
+    rest /= per_dim;
+    const double lo = limits[2 * k], hi = limits[2 * k + 1];
+    double v = lo;
+    if (per_dim > 1) {
+      const double step = (hi - lo) / (double)(per_dim - 1);
+      v = (i == per_dim - 1) ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+    }
+    out[j * d + k] = v;
+  }
+}
+}  // namespace gprc
+
+static int grid_size(int d, int per_dim, long* m) {
+  GPRC_ARG(d > 0 && per_dim > 0);
+  long t = 1;
+  for (int k = 0; k < d; ++k) {
+    if (t > (1L << 40) / per_dim) return set_error(-1, __FILE__, __LINE__, "grid too large");
+    t *= per_dim;
+  }
+  *m = t;
+  return 0;
+}
+
+extern "C" int gprc_grid_points(gprc_ctx* c, const double* limits, int d, int per_dim, double* out) {
+  GPRC_ARG(c && limits && out);
+  long m = 0;
+  GPRC_CHECK(grid_size(d, per_dim, &m));
+  DeviceGuard guard(c);
+  double *dl = nullptr, *dout = nullptr;
+  GPRC_CHECK(dmalloc(&dl, (size_t)2 * d));
+  int rc = dmalloc(&dout, (size_t)d * m);
+  if (!rc) {
+    cudaMemcpyAsync(dl, limits, sizeof(double) * 2 * d, cudaMemcpyHostToDevice, c->stream);
+    grid_points_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(dl, d, per_dim, m, dout);
+    c->launches++;
+    cudaMemcpyAsync(out, dout, sizeof(double) * d * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  }
+  dfree(dl);
+  dfree(dout);
+  return rc;
+}
+
+// $predict on the grid simulate_regression() builds (R/simulation.R:101-102) without the grid ever existing on the host
+extern "C" int gprc_gpr_predict_grid(gprc_gpr* g, const double* limits, int per_dim, double* mean, double* var) {
+  GPRC_ARG(g && limits && mean && var);
+  GPRC_ARG(!g->precomputed);
+  long m = 0;
+  GPRC_CHECK(grid_size(g->d, per_dim, &m));
+  gprc_ctx* c = g->ctx;
+  DeviceGuard guard(c);
+  double *dl = nullptr, *dXs = nullptr, *dmean = nullptr, *dvar = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dl, (size_t)2 * g->d))) break;
+    if ((rc = dmalloc(&dXs, (size_t)g->d * m))) break;
+    if ((rc = dmalloc(&dmean, (size_t)m))) break;
+    if ((rc = dmalloc(&dvar, (size_t)m))) break;
+    cudaMemcpyAsync(dl, limits, sizeof(double) * 2 * g->d, cudaMemcpyHostToDevice, c->stream);
+    grid_points_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(dl, g->d, per_dim, m, dXs);
+    c->launches++;
+    if ((rc = predict_pointwise_dev(c, g->spec.dev, g->X, g->d, g->F, g->ws, g->alpha, nullptr, dXs, m, dmean, dvar)))
+      break;
+    cudaMemcpyAsync(mean, dmean, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(var, dvar, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  dfree(dl);
+  dfree(dXs);
+  dfree(dmean);
+  dfree(dvar);
+  return rc;
+}
+
 extern "C" int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* mean, double* var) {
   GPRC_ARG(g && Xs && mean && var && m >= 0);
   GPRC_ARG(!g->precomputed);

@@ -134,6 +134,22 @@ class GPR:
     def L(self, value):
         raise AttributeError("`$L` is read only")
 
+    def predict_grid(self, limits, per_dim):
+        """$predict on the test grid simulate_regression() builds (R/simulation.R:101-102: per_dim points per dimension
+        between the limits, combined by combine_all), generated on the device (gprc_gpr_predict_grid):
+        per_dim^D x 2 matrix cbind(mean, var) in the grid's own point order."""
+        limits = np.ascontiguousarray(np.asarray(limits, dtype=np.float64).reshape(-1, 2))
+        D = self._X.shape[0]
+        if limits.shape[0] != D:
+            raise ValueError("limits must have one (lower, upper) row per dimension")
+        if kernel_spec_of(self._k) is None:
+            raise TypeError("predict_grid needs a built-in kernel (cov_func of sqrexp, ...)")
+        m = int(per_dim) ** D
+        mean, var = np.empty(m), np.empty(m)
+        _lib.check(self._ctx.lib.gprc_gpr_predict_grid(self._handle, _lib.dptr(limits), int(per_dim), _lib.dptr(mean),
+                                                       _lib.dptr(var)))
+        return np.column_stack([mean, var])
+
     def predict(self, X_star, pointwise_var=True):
         """R/GPRclass.R:155-170: m x 2 matrix cbind(mean, var), or list(mean (m x 1), cov (m x m))."""
         X_star = np.asarray(X_star, dtype=np.float64)

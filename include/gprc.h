@@ -143,6 +143,13 @@ int gprc_gpr_predict(gprc_gpr* g, const double* Xs, long m, double* mean, double
 int gprc_gpr_predict_dev(gprc_gpr* g, const double* dXs, long m, double* dmean, double* dvar);
 /* precomputed K_star (n x m) and kss = k(X_star, X_star) (m) for closure kernels */
 int gprc_gpr_predict_precomputed(gprc_gpr* g, const double* Ks, const double* kss, long m, double* mean, double* var);
+/* Test grids on the device: the points combine_all(lapply(1:d, function(k) seq(lo_k, hi_k, length.out =
+ * per_dim))) of R/simulation.R:101-102, 338-349 -- d x per_dim^d, points contiguous, first dimension slowest.
+ * limits: d x 2 (lo, hi per dimension, row-major pairs).  gprc_grid_points copies the grid to the host (tests,
+ * plotting); gprc_gpr_predict_grid predicts on it without the grid ever existing on the host. */
+int gprc_grid_points(gprc_ctx* ctx, const double* limits, int d, int per_dim, double* out);
+int gprc_gpr_predict_grid(gprc_gpr* g, const double* limits, int per_dim, double* mean, double* var);
+
 /* GPR$predict(X_star, pointwise_var = FALSE), R/GPRclass.R:167-168: mean (m), cov (m x m). */
 int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, double* mean, double* cov);
 int gprc_gpr_get(gprc_gpr* g, int what, double* host);

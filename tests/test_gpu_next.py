@@ -19,3 +19,28 @@ def test_fit_family_inside_the_library_follows_the_host_optimiser(gprc, cov):
     lib = _fit_one(obj, cov, engine="library")
     np.testing.assert_array_equal(np.atleast_1d(lib["par"]), np.atleast_1d(host["par"]))
     assert lib["value"] == float(host["value"])
+
+
+@pytest.mark.gpu_next
+@pytest.mark.parametrize("limits,per_dim", [([[-6.0, 6.0]], 1000), ([[-4.0, 4.0], [-1.0, 3.0]], 100),
+                                            ([[0.0, 1.0], [-2.0, 2.0], [5.0, 5.5]], 7), ([[1.0, 2.0]], 1)])
+def test_device_grid_is_bitwise_the_host_grid(gprc, limits, per_dim):
+    """gprc_grid_points against combine_all(seq(...)) of R/simulation.R:101-102, 338-349 as mirrored by
+    simulation._grid / combine_all on the host (numpy.linspace arithmetic)."""
+    from gprc_b200.simulation import combine_all, grid_points
+    lim = np.asarray(limits, float)
+    want = combine_all([np.linspace(lim[i, 0], lim[i, 1], per_dim) for i in range(lim.shape[0])])
+    got = grid_points(lim, per_dim)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu_next
+def test_predict_grid_equals_predict_on_the_host_grid(gprc):
+    from gprc_b200.simulation import combine_all
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-4, 4, (2, 300))
+    y = np.sin(X[0]) * np.cos(X[1]) + rng.normal(0, 0.1, 300)
+    g = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.sqrexp, l=1.0))
+    lim = np.array([[-4.0, 4.0], [-4.0, 4.0]])
+    grid = combine_all([np.linspace(lim[i, 0], lim[i, 1], 60) for i in range(2)])
+    np.testing.assert_array_equal(g.predict_grid(lim, 60), g.predict(grid))
