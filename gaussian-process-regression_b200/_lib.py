@@ -25,6 +25,7 @@ OPT_PREDICT_PATH = 2
 OPT_OZAKI_DIGITS = 3
 OPT_INT8_AUTO = 4
 OPT_INT8_TILE = 5
+OPT_INT8_TEST_SHRINK = 6
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 
 

@@ -66,6 +66,7 @@ struct gprc_ctx {
   int opt_ozaki_digits = 7;
   int opt_int8_auto = 1;
   int opt_int8_tile = 64;
+  int opt_int8_test_shrink = 0;
   int last_predict_path = 0;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};

@@ -355,6 +355,11 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     c->opt_predict_path = value;
     return 0;
   }
+  if (option == GPRC_OPT_INT8_TEST_SHRINK) {
+    GPRC_ARG(value >= 0 && value <= 60);
+    c->opt_int8_test_shrink = value;
+    return 0;
+  }
   if (option == GPRC_OPT_INT8_TILE) {
     GPRC_ARG(value == 64 || value == 128);
     c->opt_int8_tile = value;
@@ -756,7 +761,8 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   int* flag = ws.sched + 3;
   PhaseTimer t(c, GPRC_T_VAR);
   GPRC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
-  oz::colscale_kernel<<<(unsigned)((mcur_pad + 255) / 256), 256, 0, c->stream>>>(ws.kss, mcur, mcur_pad, ws.oz_ecol, ws.oz_scol);
+  oz::colscale_kernel<<<(unsigned)((mcur_pad + 255) / 256), 256, 0, c->stream>>>(ws.kss, mcur, mcur_pad, ws.oz_ecol, ws.oz_scol,
+                                                                                            c->opt_int8_test_shrink);
   c->launches++;
   for (int i = 0; i < nt; ++i) {
     if (i > 0) {
@@ -835,9 +841,16 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   int path = c->opt_predict_path;
   bool planned = (path == 0 && !F.W && m >= WAVE_COLS);  // large predict, no inverse at hand: substitution
   if (planned && c->opt_int8_auto && F.n_pad >= 4096) {
-    // ... with its products on the INT8 tensor cores once the O(n^2 m) term dominates (2x the FP64 tensor roofline)
-    planned = false;
-    path = 4;
+    // ... with its products on the INT8 tensor cores once the O(n^2 m) term dominates (2x the FP64 tensor roofline),
+    // provided the digit planes fit: S n_pad^2 bytes for L (unless already built) plus one wave of K_star^T and its digits
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const double S = (double)c->opt_ozaki_digits, np = (double)F.n_pad;
+    const double need = (F.ozLs ? 0.0 : S * np * np) + (double)WAVE_COLS * np * (8.0 + S) * 1.1;
+    if ((double)free_b + (double)c->pool_cached_bytes > need * 1.05 || ws.ozVs) {
+      planned = false;
+      path = 4;
+    }
   }
   if (path == 0 && !planned) path = 1;
   if (path == 1) GPRC_CHECK(ensure_inverse(c, F));

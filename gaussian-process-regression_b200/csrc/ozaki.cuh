@@ -156,14 +156,16 @@ __global__ void __launch_bounds__(256) split_l_kernel(const double* __restrict__
 // ---------------------------------------------------------------------------------------------------------------
 // V: per-test-point exponents from k**, digits of a freshly solved block row
 // ---------------------------------------------------------------------------------------------------------------
+// shrink > 0 (GPRC_OPT_INT8_TEST_SHRINK, tests only) lowers every exponent so that V leaves its range and the overflow
+// flag / FP64 redo of the chunk is exercised
 __global__ void colscale_kernel(const double* __restrict__ kss, long mcur, long mpad, int* __restrict__ ecol,
-                                double* __restrict__ scale_col) {
+                                double* __restrict__ scale_col, int shrink = 0) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= mpad) return;
   int e = 0;
   if (t < mcur) {
     const double b = sqrt(fmax(kss[t], 0.0)) * (1.0 + 1e-9);
-    e = exponent_of(b);
+    e = exponent_of(b) - shrink;
   }
   ecol[t] = e;
   scale_col[t] = ldexp(1.0, e - 6);

@@ -63,6 +63,8 @@ enum {
                                column maximum) or 8 */
   GPRC_OPT_INT8_AUTO = 4, /* 1 (default): the automatic choice takes path 4 where it takes the substitution today
                             (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
+  GPRC_OPT_INT8_TEST_SHRINK = 6, /* tests only: lower the per-test-point exponents of path 4 by this many bits so that
+                            v leaves its fixed-point range: the overflow flag must fire and the chunk be redone in FP64 */
   GPRC_OPT_INT8_TILE = 5 /* test points per CTA on path 4: 64 (default: all orders in one pass, 7 accumulators in
                             tensor memory) or 128 (128 x 128 x 32 MMAs at their math floor, orders in two passes; 1.4 x
                             fewer tensor-pipe cycles but 1.4 x the HBM traffic -- equal under the 1000 W cap today) */

@@ -44,3 +44,47 @@ def test_predict_grid_equals_predict_on_the_host_grid(gprc):
     lim = np.array([[-4.0, 4.0], [-4.0, 4.0]])
     grid = combine_all([np.linspace(lim[i, 0], lim[i, 1], 60) for i in range(2)])
     np.testing.assert_array_equal(g.predict_grid(lim, 60), g.predict(grid))
+
+
+@pytest.mark.gpu_next
+def test_int8_overflow_flag_redoes_the_chunk_in_fp64(gprc, ctx):
+    """Path 4 bounds |v| by sqrt(k**).  With the exponents lowered by 30 bits (test option) every block row of V overflows
+    its fixed-point range: the device flag must fire and the chunk be recomputed by the FP64 substitution, so the result
+    is the FP64 result bit for bit."""
+    rng = np.random.default_rng(36)
+    n, m = 700, 1000
+    X = rng.uniform(-2, 2, (3, n))
+    y = np.sum(np.sin(X), axis=0) + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-2, 2, (3, m))
+    g = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    out = {}
+    for path, shrink in ((2, 0), (4, 30)):
+        ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
+        ctx.set_option(gprc._lib.OPT_INT8_TEST_SHRINK, shrink)
+        try:
+            out[path] = g.predict(Xs)
+        finally:
+            ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
+            ctx.set_option(gprc._lib.OPT_INT8_TEST_SHRINK, 0)
+    np.testing.assert_array_equal(out[4], out[2])
+
+
+@pytest.mark.gpu_next
+def test_gpc_latent_prediction_on_the_int8_path(gprc, ctx):
+    """GPC$predict_class's latent mean / variance (R/GPCclass.R:110-115) go through the same variance pass with the rows of
+    K_star scaled by sqrt(W); |v| <= sqrt(k**) holds there too, so path 4 applies unchanged."""
+    rng = np.random.default_rng(37)
+    n, m = 600, 900
+    X = rng.uniform(-4, 4, (2, n))
+    y = np.where(np.abs(X[0]) + np.abs(X[1]) > 2.5, 1.0, -1.0)
+    Xs = rng.uniform(-4, 4, (2, m))
+    g = gprc.GPC(X, y, gprc.cov_func(gprc.sqrexp, l=0.5), 1e-5, verbose=False, ctx=ctx)
+    out = {}
+    for path in (2, 4):
+        ctx.set_option(gprc._lib.OPT_PREDICT_PATH, path)
+        try:
+            out[path] = np.column_stack(g.predict_latent(Xs))
+        finally:
+            ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
+    np.testing.assert_allclose(out[4][:, 0], out[2][:, 0], rtol=1e-13, atol=0)
+    assert np.max(np.abs(out[4][:, 1] - out[2][:, 1])) < 1e-12
