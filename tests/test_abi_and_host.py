@@ -240,3 +240,32 @@ def test_int8_digit_arithmetic_host_selftest():
     out = subprocess.run([tool, "digits"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count(" 0 failures") == 5, out.stdout
+
+
+@pytest.mark.parametrize("path,tile,trtri", [(4, 64, 0.0), (4, 128, 0.0), (2, 64, 0.0), (1, 64, 1200.0)])
+def test_bench_roofline_block_is_serialisable(path, tile, trtri):
+    """bench.roofline_block (pure function): the INT8 pass reports against the INT8 pipe (frac < 1) with the FP64
+    view beside it; the FP64 passes against cuBLAS Dgemm.  Guards the last lines of a minutes-long GPU run."""
+    import json
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    args = types.SimpleNamespace(ozaki_digits=7, int8_tile=tile)
+    timers = dict(build_k=9.0, chol=1240.0, solve=19.0, trtri=trtri, build_ks=400.0, var=32000.0, newton=0.0, predict=32500.0)
+    n, m = 50000, 1000000
+    flops = float(n) * n * m
+    achieved = flops / (timers["var"] * 1e-3) / 1e12
+    r = bench.roofline_block(args, path, timers, achieved, 35.5, flops, timers["var"], 34.0, n)
+    line = json.loads(json.dumps(dict(roofline=r)))["roofline"]
+    for key in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "predict_path", "ms_per_step"):
+        assert key in line, key
+    assert line["bound"] == "tensor" and line["unit"] == "TFLOP/s"
+    assert abs(line["frac"] - line["achieved"] / line["peak"]) < 1e-12
+    if path == 4:
+        assert line["frac"] < 1.0 and line["fp64_equivalent"]["frac"] > 1.5
+        assert line["int8"]["int8_products_per_fp64_product"] == 28 and ("update128" in line["kernel"]) == (tile == 128)
+    else:
+        assert "fp64_equivalent" not in line and abs(line["achieved"] - achieved) < 1e-9
+    assert bench.roofline_block(args, path, timers, None, 35.5, flops, timers["var"], 34.0, n)["frac"] is None
