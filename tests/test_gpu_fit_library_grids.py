@@ -1,10 +1,12 @@
-"""GPU tests written after this round's GPU budget was spent: not yet run on a B200, therefore NOT in the gating `gpu`
-tier.  Run them with `python -m pytest tests -m gpu_next` on a GPU box and move each green test to the `gpu` tier."""
+"""Library-side optimiser, device test grids (8f-4), the INT8 path's overflow -> FP64 redo and GPC on
+the INT8 path.  Written late in round 1 in the non-gating `gpu_next` tier, run green on a B200
+(profiles/r1_pytest_gpu_next_promoted.log: 13 passed) and promoted to the gating `gpu` tier."""
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.gpu
 
-@pytest.mark.gpu_next
+
 @pytest.mark.parametrize("cov", ["sqrexp", "gammaexp", "constant", "linear", "polynomial", "rationalquadratic"])
 def test_fit_family_inside_the_library_follows_the_host_optimiser(gprc, cov):
     """gprc_fit_family: the optimiser trajectory of R/fit.R:113-162 run inside libgprc with X, y
@@ -21,7 +23,6 @@ def test_fit_family_inside_the_library_follows_the_host_optimiser(gprc, cov):
     assert lib["value"] == float(host["value"])
 
 
-@pytest.mark.gpu_next
 @pytest.mark.parametrize("limits,per_dim", [([[-6.0, 6.0]], 1000), ([[-4.0, 4.0], [-1.0, 3.0]], 100),
                                             ([[0.0, 1.0], [-2.0, 2.0], [5.0, 5.5]], 7), ([[1.0, 2.0]], 1)])
 def test_device_grid_is_bitwise_the_host_grid(gprc, limits, per_dim):
@@ -34,7 +35,6 @@ def test_device_grid_is_bitwise_the_host_grid(gprc, limits, per_dim):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.gpu_next
 def test_predict_grid_equals_predict_on_the_host_grid(gprc):
     from gprc_b200.simulation import combine_all
     rng = np.random.default_rng(5)
@@ -46,7 +46,6 @@ def test_predict_grid_equals_predict_on_the_host_grid(gprc):
     np.testing.assert_array_equal(g.predict_grid(lim, 60), g.predict(grid))
 
 
-@pytest.mark.gpu_next
 def test_int8_overflow_flag_redoes_the_chunk_in_fp64(gprc, ctx):
     """Path 4 bounds |v| by sqrt(k**).  With the exponents lowered by 30 bits (test option) every block row of V overflows
     its fixed-point range: the device flag must fire and the chunk be recomputed by the FP64 substitution, so the result
@@ -69,7 +68,6 @@ def test_int8_overflow_flag_redoes_the_chunk_in_fp64(gprc, ctx):
     np.testing.assert_array_equal(out[4], out[2])
 
 
-@pytest.mark.gpu_next
 def test_gpc_latent_prediction_on_the_int8_path(gprc, ctx):
     """GPC$predict_class's latent mean / variance (R/GPCclass.R:110-115) go through the same variance pass with the rows of
     K_star scaled by sqrt(W); |v| <= sqrt(k**) holds there too, so path 4 applies unchanged."""
