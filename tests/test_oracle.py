@@ -139,3 +139,17 @@ def test_oracle_matches_golden_gpc_and_dens():
     got = [o.dens(GOLD["dens_X"], GOLD["dens_y"], 0.05, "rationalquadratic", list(t), minors="cholesky")
            for t in GOLD["dens_thetas"]]
     np.testing.assert_allclose(got, GOLD["dens_rq"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("S,tol", [(6, 1e-10), (7, 1e-12)])
+def test_int8_digit_scheme_accuracy_numpy_emulation(S, tol):
+    """The arithmetic of csrc/ozaki.cuh emulated in NumPy (tools/oz_sim.py): S signed 8-bit digits per entry, exact
+    digit products, pairs of order >= S dropped, Horner in FP64.  Against the FP64 triangular solve on a C4-like problem
+    (sqrexp, d = 8, noise 0.01) the predictive variance must agree far inside the north-star tolerance of 1e-9."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("oz_sim", os.path.join(root, "tools", "oz_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    dv, dvar, vmin = sim.experiment(512, 96, S)
+    assert dvar < tol and dv < 100 * tol and vmin > 0

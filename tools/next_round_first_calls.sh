@@ -1,0 +1,14 @@
+#!/bin/bash
+# The first GPU calls of the next round, in order.  Each line is one gpurun call.
+#
+# 1. the wide INT8 kernel at full C4 size (default run of the bench with --int8-tile 128); promote it to the default
+#    (opt_int8_tile = 128 in csrc/common.cuh, --int8-tile default in bench.py) if `parity` is green and `value` beats
+#    profiles/r1_bench_c4_int8_default.json (34.31 s):
+/usr/local/graft/bin/gpurun --timeout 420 -- \
+  'timeout 400 python bench.py --int8-tile 128 > gpurun_out/bench_c4_tile128.json 2> gpurun_out/bench_c4_tile128.err; tail -c 400 gpurun_out/bench_c4_tile128.err; head -c 900 gpurun_out/bench_c4_tile128.json'
+# 2. the full GPU tier on the then-current default:
+/usr/local/graft/bin/gpurun --timeout 300 -- \
+  'timeout 280 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log'
+# 3. 8 GPUs, C4 (charged 8x): scaling of train (distributed Cholesky) + INT8 predict per shard
+/usr/local/graft/bin/gpurun --gpus 8 --timeout 300 -- \
+  'timeout 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 1 --warmup 3 > gpurun_out/bench_c4_8gpu_int8.json 2> gpurun_out/bench_c4_8gpu_int8.err; head -c 900 gpurun_out/bench_c4_8gpu_int8.json'
