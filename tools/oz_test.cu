@@ -1,7 +1,7 @@
 // oz_test.cu -- standalone check of the INT8 (tcgen05) substitution update of csrc/ozaki.cuh against (a) a host
 // emulation of exactly the same digit arithmetic and (b) the plain FP64 product; plus a timing mode.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/oz_test tools/oz_test.cu
-//   tools/oz_test check|time <S> <n> <mc> <i> [ts 0 [dbg]]   (ts = 1: A operand from tensor memory)   tools/oz_test digits
+//   tools/oz_test check|time <S> <n> <mc> <i> [ts 0 [dbg]]   (ts = 1: A operand from tensor memory, 2: wide 128 x 128 kernel, 3: CTA-pair kernel, i = pair index)   tools/oz_test digits
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "../gaussian-process-regression_b200/csrc/ozaki.cuh"
+#include "../gaussian-process-regression_b200/csrc/ozaki_pair.cuh"  // not yet run on hardware (mode 3)
 
 namespace gprc {
 thread_local std::string g_last_error;
@@ -36,7 +37,7 @@ __global__ void clock_probe(long long* out) {
   out[1] = (long long)(t1 - t0);
 }
 
-template <int S, bool TS, bool WIDE = false>
+template <int S, bool TS, bool WIDE = false, bool PAIR = false>
 static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, int dbg) {
   const long n_pad = n, KB = n_pad / 32;
   std::mt19937_64 rng(12345);
@@ -72,8 +73,9 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   oz::rowmax_kernel<<<nt, 256>>>(dL, n_pad, derow, dsr);
   oz::split_l_kernel<S><<<dim3(4 * nt, nt), 256>>>(dL, n_pad, derow, dLs, (int)KB, derr);
   oz::colscale_kernel<<<(unsigned)((mc + 255) / 256), 256>>>(dkss, mc, mc, decol, dsc);
-  for (int b = 0; b < i; ++b) {
-    if constexpr (WIDE) oz::split_v128_kernel<S><<<dim3((unsigned)(mc / 128), 4), 256>>>(dT, mc, b, decol, dVs, (int)KB, derr);
+  const int rows_done = PAIR ? 2 * i : i;  // block rows of V that exist before the update under test
+  for (int b = 0; b < rows_done; ++b) {
+    if constexpr (WIDE || PAIR) oz::split_v128_kernel<S><<<dim3((unsigned)(mc / 128), 4), 256>>>(dT, mc, b, decol, dVs, (int)KB, derr);
     else oz::split_v_kernel<S><<<dim3((unsigned)(mc / 64), 4), 128>>>(dT, mc, b, decol, dVs, (int)KB, derr);
   }
   CK(cudaDeviceSynchronize());
@@ -82,10 +84,15 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   printf("split done, overflow flag = %d\n", herr);
 
   auto launch = [&](const oz::UpdateParams& q) {
-    if constexpr (WIDE) oz::update128_kernel<S><<<(unsigned)(mc / 128), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES>>>(q);
+    if constexpr (PAIR) oz::update_pair_kernel<S><<<(unsigned)(2 * (mc / 128)), oz::THREADS, oz::CfgPair<S>::SMEM_BYTES>>>(q);
+    else if constexpr (WIDE) oz::update128_kernel<S><<<(unsigned)(mc / 128), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES>>>(q);
     else oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(q);
   };
-  if constexpr (WIDE) {
+  if constexpr (PAIR) {
+    CK(cudaFuncSetAttribute(oz::update_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::CfgPair<S>::SMEM_BYTES));
+    printf("pair kernel: clusters of 2 CTAs, 256 x 128 tiles (block rows %d and %d against k < %d), ring %d B, stages %d / %d\n",
+           2 * i, 2 * i + 1, 256 * i, oz::CfgPair<S>::RING, oz::CfgPair<S>::STAGES0, oz::CfgPair<S>::STAGES1);
+  } else if constexpr (WIDE) {
     CK(cudaFuncSetAttribute(oz::update128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg2<S>::SMEM_BYTES));
     printf("wide kernel: 128 x 128 tiles, two order passes, ring %d B, stages %d / %d\n", oz::Cfg2<S>::RING,
            oz::Cfg2<S>::STAGES0, oz::Cfg2<S>::STAGES1);
@@ -125,7 +132,7 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
         if (kt < 24 || (kt >= 200 && kt < 216) || (kt >= 250 && kt < 266))
           printf("  %3d %9lld %9lld %9lld\n", kt, tr[kt * 4] - t0, tr[kt * 4 + 1] - t0, tr[kt * 4 + 2] - t0);
     }
-    const double K = 128.0 * i, flops = 2.0 * 128 * mc * K;
+    const double K = (PAIR ? 256.0 : 128.0) * i, flops = 2.0 * (PAIR ? 256 : 128) * mc * K;
     long long* dclk;
     CK(cudaMalloc(&dclk, 16));
     clock_probe<<<1, 1>>>(dclk);
@@ -134,7 +141,7 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     const double mhz = (double)hclk[0] / (double)hclk[1] * 1e3;
     printf("update_kernel<%d,%s%s> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
            "%.0f clk per k-step\n", S, TS ? "TS" : "SS", WIDE ? " wide" : "", dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
-           ms * 1e-3 * mhz * 1e6 / (4.0 * i) / ((mc / (WIDE ? 128 : 64) + 147) / 148));
+           ms * 1e-3 * mhz * 1e6 / ((PAIR ? 8.0 : 4.0) * i) / ((mc / (WIDE ? 128 : (PAIR ? 64 : 64)) + 147) / 148));
     return 0;
   }
 
@@ -144,12 +151,14 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     printf("update kernel failed: %s\n", cudaGetErrorString(e));
     return 3;
   }
-  std::vector<double> got((size_t)128 * mc);
-  CK(cudaMemcpy2D(got.data(), mc * 8, dT + (size_t)i * 128 * mc, mc * 8, mc * 8, 128, cudaMemcpyDeviceToHost));
+  const int nrows = PAIR ? 256 : 128;
+  const long row0 = PAIR ? 256L * i : 128L * i;
+  std::vector<double> got((size_t)nrows * mc);
+  CK(cudaMemcpy2D(got.data(), mc * 8, dT + (size_t)row0 * mc, mc * 8, mc * 8, nrows, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
 
   // host emulation of the same digits
-  const long K = 128L * i;
+  const long K = PAIR ? 256L * i : 128L * i;
   std::vector<int> erow(n_pad), ecol(mc);
   for (long r = 0; r < n_pad; ++r) {
     double mx = 0;
@@ -168,8 +177,8 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   long bad = 0;
   std::vector<long long> acc((size_t)S * mc);
   std::vector<double> ref(mc);
-  for (int r = 0; r < 128; ++r) {
-    const long row = 128L * i + r;
+  for (int r = 0; r < nrows; ++r) {
+    const long row = row0 + r;
     std::fill(acc.begin(), acc.end(), 0LL);
     std::fill(ref.begin(), ref.end(), 0.0);
     for (long k = 0; k < K; ++k) {
@@ -206,7 +215,8 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     }
   }
   printf("RESULT S=%d %s%s i=%d: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
-         S, TS ? "TS" : "SS", WIDE ? " wide" : "", i, herr, max_emul, bad, 128 * mc, max_fp64, max_ref, bad == 0 ? "  OK" : "  FAIL");
+         S, TS ? "TS" : "SS", PAIR ? " pair" : (WIDE ? " wide" : ""), i, herr, max_emul, bad, (long)nrows * mc, max_fp64, max_ref,
+         bad == 0 ? "  OK" : "  FAIL");
   return bad == 0 ? 0 : 1;
 }
 
@@ -340,16 +350,18 @@ int main(int argc, char** argv) {
   const int i = atoi(argv[5]);
   const uint32_t lbo = argc > 7 ? (uint32_t)atoi(argv[6]) : 0u, sbo = 0u;  // argv[6] = 1 selects the TS kernel
   const int dbg = argc > 8 ? atoi(argv[8]) : 0;
-  if (n % 128 || mc % 128 || i < 1 || i >= n / 128) {
+  if (n % 128 || mc % 128 || i < 1 || i >= n / 128 || (argc > 7 && atoi(argv[6]) == 3 && 2 * i + 1 >= n / 128)) {
     printf("bad sizes\n");
     return 64;
   }
   switch (S) {
     case 1: return (lbo == 1 ? run<1, true>(timing, n, mc, i, lbo, sbo, dbg) : run<1, false>(timing, n, mc, i, lbo, sbo, dbg));
     case 2: return (lbo == 1 ? run<2, true>(timing, n, mc, i, lbo, sbo, dbg) : run<2, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 6: return (lbo == 2 ? run<6, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+    case 6: return (lbo == 3 ? run<6, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                             : lbo == 2 ? run<6, false, true>(timing, n, mc, i, lbo, sbo, dbg)
                              : lbo == 1 ? run<6, true>(timing, n, mc, i, lbo, sbo, dbg) : run<6, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 7: return (lbo == 2 ? run<7, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+    case 7: return (lbo == 3 ? run<7, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                             : lbo == 2 ? run<7, false, true>(timing, n, mc, i, lbo, sbo, dbg)
                              : lbo == 1 ? run<7, true>(timing, n, mc, i, lbo, sbo, dbg) : run<7, false>(timing, n, mc, i, lbo, sbo, dbg));
     case 8: return (lbo == 2 ? run<8, false, true>(timing, n, mc, i, lbo, sbo, dbg) : run<8, false>(timing, n, mc, i, lbo, sbo, dbg));
   }
