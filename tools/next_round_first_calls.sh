@@ -1,6 +1,9 @@
 #!/bin/bash
 # The first GPU calls of the next round, in order.  Each line is one gpurun call.
 #
+# 0. the non-gating tier (tests written without GPU time): python -m pytest tests -m gpu_next; promote green tests
+/usr/local/graft/bin/gpurun --timeout 200 -- \
+  'timeout 180 python -m pytest tests -m gpu_next -v > gpurun_out/pytest_gpu_next.log 2>&1; tail -8 gpurun_out/pytest_gpu_next.log'
 # 1. the wide INT8 kernel at full C4 size (default run of the bench with --int8-tile 128); promote it to the default
 #    (opt_int8_tile = 128 in csrc/common.cuh, --int8-tile default in bench.py) if `parity` is green and `value` beats
 #    profiles/r1_bench_c4_int8_default.json (34.31 s):
