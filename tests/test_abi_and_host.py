@@ -269,3 +269,33 @@ def test_bench_roofline_block_is_serialisable(path, tile, trtri):
     else:
         assert "fp64_equivalent" not in line and abs(line["achieved"] - achieved) < 1e-9
     assert bench.roofline_block(args, path, timers, None, 35.5, flops, timers["var"], 34.0, n)["frac"] is None
+
+
+def _load_protocol_sim(mutate=None):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "tools", "oz_protocol_sim.py")).read()
+    if mutate is not None:
+        old, new = mutate
+        assert old in src
+        src = src.replace(old, new)
+    ns = {}
+    exec(compile(src, "oz_protocol_sim", "exec"), ns)
+    return ns
+
+
+def test_int8_kernel_barrier_protocols_model():
+    """tools/oz_protocol_sim.py: the producer / MMA / relay / drain roles of the three INT8 kernels (default, wide, and the
+    CTA-pair draft that has not run on hardware) replayed with the kernels' slot / phase / count arithmetic under random
+    latencies: no deadlock, every MMA reads the k-step it expects in every CTA, no stage overwritten or ring re-partitioned
+    under outstanding reads, accumulators never written during a drain."""
+    assert _load_protocol_sim()["campaign"](12) == []
+
+
+@pytest.mark.parametrize("mutation", [
+    ('            if passes == 2 and r > 0:\n                yield ("wait", pass_done[c], (r - 1) & 1)', "            pass"),
+    ("                if need_wait:", "                if False:"),
+    ('                if ncta == 2:\n                    yield ("wait", peer_ready', '                if False:\n                    yield ("wait", peer_ready'),
+])
+def test_protocol_model_detects_injected_bugs(mutation):
+    """The model must have teeth: dropping the pass_done wait, the empty wait or the peer relay wait is caught."""
+    assert len(_load_protocol_sim(mutation)["campaign"](6)) > 0
