@@ -288,7 +288,7 @@ def test_int8_kernel_barrier_protocols_model():
     CTA-pair draft that has not run on hardware) replayed with the kernels' slot / phase / count arithmetic under random
     latencies: no deadlock, every MMA reads the k-step it expects in every CTA, no stage overwritten or ring re-partitioned
     under outstanding reads, accumulators never written during a drain."""
-    assert _load_protocol_sim()["campaign"](12) == []
+    assert _load_protocol_sim()["campaign"](10) == []
 
 
 @pytest.mark.parametrize("mutation", [
@@ -298,4 +298,4 @@ def test_int8_kernel_barrier_protocols_model():
 ])
 def test_protocol_model_detects_injected_bugs(mutation):
     """The model must have teeth: dropping the pass_done wait, the empty wait or the peer relay wait is caught."""
-    assert len(_load_protocol_sim(mutation)["campaign"](6)) > 0
+    assert len(_load_protocol_sim(mutation)["campaign"](3)) > 0

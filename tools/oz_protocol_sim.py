@@ -69,7 +69,7 @@ class Sim:
                 poll()
         self.at(0.0, step)
 
-    def run(self, limit=2_000_000):
+    def run(self, limit=150_000):
         steps = 0
         while self.q and steps < limit:
             self.t, _, fn = heapq.heappop(self.q)
