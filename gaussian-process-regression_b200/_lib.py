@@ -48,6 +48,7 @@ SIGNATURES = {
     "gprc_ctx_free": (None, [_P]),
     "gprc_ctx_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
     "gprc_ctx_sync": (C.c_int, [_P]),
+    "gprc_ctx_set_interrupt": (C.c_int, [_P, C.CFUNCTYPE(C.c_int, C.c_void_p), _P]),
     "gprc_ctx_reset_timers": (None, [_P]),
     "gprc_ctx_get_timers": (C.c_int, [_P, c_double_p, c_long_p]),
     "gprc_ctx_last_predict_path": (C.c_int, [_P]),

@@ -68,6 +68,8 @@ struct gprc_ctx {
   int opt_int8_tile = 64;
   int opt_int8_test_shrink = 0;
   int last_predict_path = 0;
+  gprc_interrupt_fn interrupt_fn = nullptr;  // polled between chunks of a long predict
+  void* interrupt_user = nullptr;
   long launches = 0;
   double timers[GPRC_T_COUNT] = {0};
   // pending (start, stop, phase) events; resolved lazily in gprc_ctx_get_timers so that timing never adds a sync

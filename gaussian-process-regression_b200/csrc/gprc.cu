@@ -377,6 +377,20 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
   return set_error(-1, __FILE__, __LINE__, "unknown option");
 }
 
+extern "C" int gprc_ctx_set_interrupt(gprc_ctx* c, gprc_interrupt_fn fn, void* user) {
+  GPRC_ARG(c != nullptr);
+  c->interrupt_fn = fn;
+  c->interrupt_user = user;
+  return 0;
+}
+
+// between chunks of a long call: has the host asked to stop?  (drains the stream first so that nothing is left running)
+static int poll_interrupt(gprc_ctx* c) {
+  if (!c->interrupt_fn || !c->interrupt_fn(c->interrupt_user)) return 0;
+  cudaStreamSynchronize(c->stream);
+  return set_error(-8, __FILE__, __LINE__, "interrupted");
+}
+
 extern "C" int gprc_ctx_sync(gprc_ctx* c) {
   GPRC_ARG(c != nullptr);
   DeviceGuard g(c);
@@ -867,6 +881,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     long c0 = 0;
     for (long left = tiles - last_tiles; left > 0;) {
       const long take = std::min(left, cap_tiles);
+      if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
       GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(take * NB, m - c0), 2, dmean, dvar));
       c0 += take * NB;
       left -= take;
@@ -903,6 +918,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 75.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad));
     for (long c0 = 0; c0 < m; c0 += ws.mc) {
       const long mcur = std::min(ws.mc, m - c0);
+      if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
       GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 4, dmean, dvar));
       GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       GPRC_CUDA(cudaStreamSynchronize(c->stream));
@@ -917,8 +933,10 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   // Running several chunk pipelines on concurrent streams was measured and does NOT recover it (2 pipelines 33.45 vs
   // 33.40 TFLOP/s, 4 sub-wave pipelines 32.4, 8: 31.4 -- the block scheduler does not pack the grids); path 3 does.
   GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
-  for (long c0 = 0; c0 < m; c0 += ws.mc)
+  for (long c0 = 0; c0 < m; c0 += ws.mc) {
+    if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
     GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, std::min(ws.mc, m - c0), path, dmean, dvar));
+  }
   return 0;
 }
 

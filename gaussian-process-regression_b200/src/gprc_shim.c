@@ -17,12 +17,19 @@
 
 static gprc_ctx* g_ctx = NULL;
 
+/* A pending Ctrl-C is detected WITHOUT long-jumping through library frames: R_CheckUserInterrupt runs inside
+ * R_ToplevelExec, which returns FALSE if it jumped.  The library polls this between chunks of a long predict and returns
+ * -8; the entry point then releases what it holds and raises the interrupt from shim level. */
+static void check_interrupt_body(void* unused) { (void)unused; R_CheckUserInterrupt(); }
+static int interrupt_pending(void* unused) { (void)unused; return R_ToplevelExec(check_interrupt_body, NULL) == FALSE; }
+
 static gprc_ctx* ctx(void) {
   if (!g_ctx) {
     int dev = 0;
     SEXP opt = Rf_GetOption1(Rf_install("gprc.device"));
     if (opt != R_NilValue) dev = Rf_asInteger(opt);
     if (gprc_ctx_create(&g_ctx, dev) != 0) Rf_error("gprc: %s", gprc_last_error());
+    gprc_ctx_set_interrupt(g_ctx, interrupt_pending, NULL);
   }
   return g_ctx;
 }

@@ -104,6 +104,12 @@ int gprc_ctx_create(gprc_ctx** out, int device);
 void gprc_ctx_free(gprc_ctx* ctx);
 int gprc_ctx_set_option(gprc_ctx* ctx, int option, int value);
 int gprc_ctx_sync(gprc_ctx* ctx);
+/* Long predicts poll `fn(user)` between chunks of test points (every few hundred ms at n = 50k); a non-zero return
+ * abandons the call with status -8 ("interrupted") after the queued work has drained.  The R shim installs a callback
+ * that asks R for a pending user interrupt without long-jumping (R_ToplevelExec around R_CheckUserInterrupt), SURVEY.md 8b.
+ * fn = NULL removes it. */
+typedef int (*gprc_interrupt_fn)(void* user);
+int gprc_ctx_set_interrupt(gprc_ctx* ctx, gprc_interrupt_fn fn, void* user);
 void gprc_ctx_reset_timers(gprc_ctx* ctx);
 int gprc_ctx_get_timers(gprc_ctx* ctx, double* ms /* GPRC_T_COUNT */, long* kernel_launches);
 /* user event pair on the library's stream: device-side timing of an arbitrary region (bench.py) */

@@ -40,4 +40,6 @@ void R_ClearExternalPtr(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 char* R_alloc(size_t, int);
+void R_CheckUserInterrupt(void);
+Rboolean R_ToplevelExec(void (*fun)(void*), void* data);
 #endif

@@ -29,3 +29,28 @@ def test_int8_substitution_with_several_drain_rounds(gprc, ctx, digits, tile):
             ctx.set_option(gprc._lib.OPT_INT8_TILE, 64)
     np.testing.assert_allclose(out[4][:, 0], out[2][:, 0], rtol=1e-13, atol=0)
     assert np.max(np.abs(out[4][:, 1] - out[2][:, 1])) < 1e-11
+
+
+@pytest.mark.gpu_next
+def test_long_predict_polls_the_interrupt_callback(gprc, ctx):
+    """gprc_ctx_set_interrupt: polled between chunks of test points; a non-zero answer abandons the call
+    with status -8 and leaves the context usable."""
+    import ctypes as C
+    rng = np.random.default_rng(39)
+    n, m = 300, (1 << 20) + 5000          # the chunk capacity is capped at 2^20 test points: two chunks
+    X = rng.uniform(-6, 6, (1, n))
+    y = 0.1 * X[0] ** 3 + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-6, 6, (1, m))
+    g = gprc.GPR(X, y, 0.01, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    calls = []
+    cb_type = C.CFUNCTYPE(C.c_int, C.c_void_p)
+    cb = cb_type(lambda user: (calls.append(1), 1)[1])
+    gprc._lib.check(ctx.lib.gprc_ctx_set_interrupt(ctx.handle, cb, None))
+    try:
+        with pytest.raises(gprc._lib.GprcError, match="interrupted"):
+            g.predict(Xs)
+    finally:
+        gprc._lib.check(ctx.lib.gprc_ctx_set_interrupt(ctx.handle, C.cast(None, cb_type), None))
+    assert len(calls) == 1
+    out = g.predict(Xs[:, :1000])         # the context and the model still work
+    assert np.all(np.isfinite(out))
