@@ -887,6 +887,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
       left -= take;
     }
     if (last_tiles > 0) {
+      if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
       GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, m - c0, 3, dmean, dvar));
       GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       GPRC_CUDA(cudaStreamSynchronize(c->stream));
