@@ -153,3 +153,29 @@ def test_int8_digit_scheme_accuracy_numpy_emulation(S, tol):
     spec.loader.exec_module(sim)
     dv, dvar, vmin = sim.experiment(512, 96, S)
     assert dvar < tol and dv < 100 * tol and vmin > 0
+
+
+@pytest.mark.parametrize("S", [6, 7, 8])
+def test_numpy_emulation_uses_the_kernels_digits(S):
+    """tools/oz_sim.py (NumPy) and csrc/ozaki.cuh (compiled for the host by tools/oz_test) must split a number into the
+    same digits: the emulation's accuracy result then speaks for the kernel, which tools/oz_test pins to these digit
+    functions bit for bit on the GPU."""
+    import importlib.util
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "oz_test")
+    if not os.path.exists(tool):
+        pytest.skip("tools/oz_test not built")
+    spec = importlib.util.spec_from_file_location("oz_sim", os.path.join(root, "tools", "oz_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    rng = np.random.default_rng(S)
+    e = 3
+    x = np.concatenate([rng.uniform(-8, 8, 40), [0.0, 7.999999, -7.999999, 1e-12, -3e-7, 0.5, -0.5]])
+    out = subprocess.run([tool, "digitsof", str(S), str(e)] + ["%.17g" % v for v in x], capture_output=True, text=True,
+                         timeout=60)
+    assert out.returncode == 0, out.stderr
+    rows = np.array([[int(t) for t in line.split()] for line in out.stdout.strip().splitlines()])
+    assert not rows[:, 0].any()                                  # no overflow flags
+    want = np.stack([d for d in sim.digits(x, np.full(len(x), e), S)], axis=1).astype(int)
+    np.testing.assert_array_equal(rows[:, 1:], want)

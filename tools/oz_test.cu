@@ -325,6 +325,25 @@ static int digits_selftest() {
 int main(int argc, char** argv) {
   if (argc >= 2 && std::string(argv[1]) == "digits")
     return digits_selftest<6>() | digits_selftest<7>() | digits_selftest<8>() | digits_selftest<1>() | digits_selftest<2>();
+  if (argc >= 5 && std::string(argv[1]) == "digitsof") {  // digitsof S e x...: the digits the kernels would use (host)
+    const int S = atoi(argv[2]), e = atoi(argv[3]);
+    for (int a = 4; a < argc; ++a) {
+      const double x = strtod(argv[a], nullptr);
+      bool ovf = false;
+      long long Y = 0;
+      int d[8] = {0};
+      switch (S) {
+        case 6: Y = oz::biased<6>(oz::to_fixed<6>(x, e, &ovf)); for (int s = 0; s < 6; ++s) d[s] = oz::digit<6>(Y, s); break;
+        case 7: Y = oz::biased<7>(oz::to_fixed<7>(x, e, &ovf)); for (int s = 0; s < 7; ++s) d[s] = oz::digit<7>(Y, s); break;
+        case 8: Y = oz::biased<8>(oz::to_fixed<8>(x, e, &ovf)); for (int s = 0; s < 8; ++s) d[s] = oz::digit<8>(Y, s); break;
+        default: printf("S must be 6, 7 or 8\n"); return 64;
+      }
+      printf("%d", ovf ? 1 : 0);
+      for (int s = 0; s < S; ++s) printf(" %d", d[s]);
+      printf("\n");
+    }
+    return 0;
+  }
   if (argc >= 2 && std::string(argv[1]) == "rate") {
     mma_rate<32, false>(1, 1);
     mma_rate<64, false>(1, 1);
