@@ -25,6 +25,7 @@ OPT_PREDICT_PATH = 2
 OPT_OZAKI_DIGITS = 3
 OPT_INT8_AUTO = 4
 OPT_INT8_TILE = 5
+INT8_TILE_DEFAULT = 64  # kernel variant of the INT8 pass the library starts with (csrc/common.cuh: opt_int8_tile)
 OPT_INT8_TEST_SHRINK = 6
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 
@@ -52,6 +53,7 @@ SIGNATURES = {
     "gprc_ctx_reset_timers": (None, [_P]),
     "gprc_ctx_get_timers": (C.c_int, [_P, c_double_p, c_long_p]),
     "gprc_ctx_last_predict_path": (C.c_int, [_P]),
+    "gprc_ctx_last_predict_chunks": (C.c_long, [_P]),
     "gprc_ctx_mark": (C.c_int, [_P, C.c_int]),
     "gprc_ctx_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, c_double_p]),
     "gprc_last_error": (C.c_char_p, []),
@@ -116,6 +118,7 @@ SIGNATURES = {
     "gprc_dev_dgemm": (C.c_int, [_P, C.c_int, C.c_long, C.c_long, C.c_long, C.c_double, _P, C.c_long, _P, C.c_long,
                                  C.c_double, _P, C.c_long]),
     "gprc_dev_trtri": (C.c_int, [_P, _P, C.c_long, C.c_long, _P, _P, _P]),
+    "gprc_dev_int8_rate": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -193,6 +196,9 @@ class Context:
 
     def last_predict_path(self):
         return int(self.lib.gprc_ctx_last_predict_path(self.handle))
+
+    def last_predict_chunks(self):
+        return int(self.lib.gprc_ctx_last_predict_chunks(self.handle))
 
     def mark(self, slot):
         check(self.lib.gprc_ctx_mark(self.handle, slot))

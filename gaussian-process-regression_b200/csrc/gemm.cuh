@@ -464,6 +464,8 @@ struct TrsmLeftUpdatePolicy {
   double* T;
   long ldt;
   int i;
+  int k0 = 0;  // first block column of the product: R_i -= L[i, k0 .. i) V[k0 .. i)  (k0 > 0: the in-pair step of the
+               // INT8 pass, whose tensor-core update stopped at the pair boundary)
   struct Tile {
     double* C;  // element (m, n) of the tile at C[n + m * ldt]
   };
@@ -473,7 +475,7 @@ struct TrsmLeftUpdatePolicy {
     w.lda = ldl;
     w.B = T + (long)tc * NB;  // element (k, n) = V[k, t] = T[t + k * ldt]
     w.ldb = ldt;
-    w.k_begin = 0;
+    w.k_begin = k0 * NB;
     w.k_end = i * NB;
     t.C = T + (long)tc * NB + (long)i * NB * ldt;
     return true;

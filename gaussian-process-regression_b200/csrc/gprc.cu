@@ -361,7 +361,7 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     return 0;
   }
   if (option == GPRC_OPT_INT8_TILE) {
-    GPRC_ARG(value == 64 || value == 128);
+    GPRC_ARG(value == 1 || value == 2 || value == 64 || value == 128);
     c->opt_int8_tile = value;
     return 0;
   }
@@ -429,6 +429,7 @@ extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
 }
 
 extern "C" int gprc_ctx_last_predict_path(gprc_ctx* c) { return c ? c->last_predict_path : 0; }
+extern "C" long gprc_ctx_last_predict_chunks(gprc_ctx* c) { return c ? c->last_predict_chunks : 0; }
 
 extern "C" int gprc_ctx_mark(gprc_ctx* c, int slot) {
   GPRC_ARG(c != nullptr && slot >= 0 && slot < 8);
@@ -751,15 +752,39 @@ static int oz_factor_digits(gprc_ctx* c, FactorState& F) {
   return 0;
 }
 
+// launch of the stacked-plane kernel on clusters of two CTAs (ozaki.cuh): pair j = block rows 2 j, 2 j + 1
+template <int S>
+static int launch_update_stack_pair(gprc_ctx* c, const oz::UpdateParams& up, long mcur_pad) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (mcur_pad / oz::BN)));
+  cfg.blockDim = dim3(oz::THREADS);
+  cfg.dynamicSmemBytes = oz::Cfg<S>::SMEM_BYTES;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  GPRC_CUDA(cudaLaunchKernelEx(&cfg, oz::update_stack_kernel<S, 2>, up));
+  return 0;
+}
+
 template <int S>
 static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, long mcur, long mcur_pad) {
   static bool configured[64] = {false};
   if (!configured[c->device & 63]) {
     GPRC_CUDA(cudaFuncSetAttribute(oz::update_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
     GPRC_CUDA(cudaFuncSetAttribute(oz::update128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg2<S>::SMEM_BYTES));
+    GPRC_CUDA(cudaFuncSetAttribute(oz::update_stack_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    GPRC_CUDA(cudaFuncSetAttribute(oz::update_stack_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
     configured[c->device & 63] = true;
   }
-  const bool wide = c->opt_int8_tile == 128;  // 128 x 128 tiles, orders in two passes (ozaki.cuh, update128_kernel)
+  // kernel variant (GPRC_OPT_INT8_TILE): 2 = stacked planes on cluster pairs, 1 = stacked planes, 64 = one MMA per digit
+  // pair (round 1), 128 = 128 x 128 tiles with the orders in two passes (round 1)
+  const int variant = c->opt_int8_tile;
+  const bool wide = variant == 128;
   GPRC_CHECK(oz_factor_digits<S>(c, F));
   const size_t need = (size_t)ws.mc * F.n_pad * S;
   if (ws.oz_bytes < need) {
@@ -778,24 +803,61 @@ static int variance_pass_ozaki_t(gprc_ctx* c, FactorState& F, PredictWorkspace& 
   oz::colscale_kernel<<<(unsigned)((mcur_pad + 255) / 256), 256, 0, c->stream>>>(ws.kss, mcur, mcur_pad, ws.oz_ecol, ws.oz_scol,
                                                                                             c->opt_int8_test_shrink);
   c->launches++;
+  auto split_row = [&](int i) {
+    if (wide)
+      oz::split_v128_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN2), 4), 256, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
+    else
+      oz::split_v_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN), 4), 128, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
+    c->launches++;
+  };
+  auto diag_row = [&](int i) {
+    TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};
+    return launch_gemm(c, dg, dim3((unsigned)ntc));
+  };
+  if (variant == 2) {
+    // block rows in pairs: one INT8 launch brings rows 2 j and 2 j + 1 up to k < 256 j (each V digit tile is fetched once
+    // for both); the 128 x 128 block L[2j+1, 2j] that remains inside the pair is applied in FP64 between the two
+    // diagonal solves
+    for (int j = 0; 2 * j < nt; ++j) {
+      const int i0 = 2 * j, i1 = 2 * j + 1;
+      const bool has1 = i1 < nt;
+      if (j > 0) {
+        if (has1) {
+          oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, j, KB, flag, 0, nullptr};
+          GPRC_CHECK(launch_update_stack_pair<S>(c, up, mcur_pad));
+        } else {  // odd number of block rows: the last one alone
+          oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i0, KB, flag, 0, nullptr};
+          oz::update_stack_kernel<S, 1><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
+        }
+        c->launches++;
+      }
+      GPRC_CHECK(diag_row(i0));
+      if (has1) {
+        TrsmLeftUpdatePolicy in_pair{F.L, F.n_pad, ws.Ks, ws.mc, i1, i0};
+        GPRC_CHECK(launch_gemm(c, in_pair, dim3((unsigned)ntc)));
+        GPRC_CHECK(diag_row(i1));
+      }
+      if (i1 + 1 < nt) {
+        split_row(i0);
+        split_row(i1);
+      }
+    }
+    GPRC_CUDA(cudaGetLastError());
+    return 0;
+  }
   for (int i = 0; i < nt; ++i) {
     if (i > 0) {
       oz::UpdateParams up{F.ozLs, ws.ozVs, F.oz_srow, ws.oz_scol, ws.Ks, ws.mc, i, KB, flag, 0, nullptr};
       if (wide)
         oz::update128_kernel<S><<<(unsigned)(mcur_pad / oz::BN2), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES, c->stream>>>(up);
+      else if (variant == 1)
+        oz::update_stack_kernel<S, 1><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
       else
         oz::update_kernel<S, false><<<(unsigned)(mcur_pad / oz::BN), oz::THREADS, oz::Cfg<S>::SMEM_BYTES, c->stream>>>(up);
       c->launches++;
     }
-    TrsmLeftDiagPolicy dg{F.dinv + (long)i * NB * NB, ws.Ks, ws.mc, i, ws.pvar, ws.mc};
-    GPRC_CHECK(launch_gemm(c, dg, dim3((unsigned)ntc)));
-    if (i + 1 < nt) {
-      if (wide)
-        oz::split_v128_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN2), 4), 256, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
-      else
-        oz::split_v_kernel<S><<<dim3((unsigned)(mcur_pad / oz::BN), 4), 128, 0, c->stream>>>(ws.Ks, ws.mc, i, ws.oz_ecol, ws.ozVs, KB, flag);
-      c->launches++;
-    }
+    GPRC_CHECK(diag_row(i));
+    if (i + 1 < nt) split_row(i);
   }
   GPRC_CUDA(cudaGetLastError());
   return 0;
@@ -823,6 +885,8 @@ static int predict_chunk(gprc_ctx* c, const KSpecDev& k, const double* dX, int d
                          const double* weights, const double* rowscale, const double* dXs, long c0, long mcur,
                          int path /* 1 inverse, 2 substitution, 3 persistent substitution, 4 INT8 substitution */, double* dmean,
                          double* dvar) {
+  GPRC_ARG(mcur > 0 && mcur <= w.mc);  // the chunk must fit the workspace (Ks, pmean, pvar, kss are n_pad x w.mc)
+  c->last_predict_chunks++;
   const long mpad = round_up(mcur, NB);
   int mean_tile = CT;  // training points per partial of the mean: 64 (direct build) or 128 (tensor-core build)
   {
@@ -869,6 +933,7 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
   if (path == 0 && !planned) path = 1;
   if (path == 1) GPRC_CHECK(ensure_inverse(c, F));
   c->last_predict_path = planned ? 2 : path;
+  c->last_predict_chunks = 0;
   PhaseTimer span(c, GPRC_T_PREDICT);
   if (planned) {
     // Mixed plan.  Whole waves of 148 tiles go through the multi-launch substitution (all CTAs sweep the same block row
@@ -887,12 +952,18 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
       left -= take;
     }
     if (last_tiles > 0) {
-      if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
-      GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, m - c0, 3, dmean, dvar));
-      GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      GPRC_CUDA(cudaStreamSynchronize(c->stream));
-      if (*reinterpret_cast<int*>(c->h_info) != 0)
-        return set_error(-6, __FILE__, __LINE__, "persistent substitution kernel: a tile dependency never arrived");
+      // the merged tail (148 + r tiles, or r tiles) in pieces of at most cap_tiles: when device memory is short the
+      // workspace may hold less than the tail (cap_tiles can be as small as one tile)
+      while (c0 < m) {
+        if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
+        const long mcur = std::min(cap_tiles * NB, m - c0);
+        GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 3, dmean, dvar));
+        c0 += mcur;
+        GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GPRC_CUDA(cudaStreamSynchronize(c->stream));
+        if (*reinterpret_cast<int*>(c->h_info) != 0)
+          return set_error(-6, __FILE__, __LINE__, "persistent substitution kernel: a tile dependency never arrived");
+      }
     }
     return 0;
   }
@@ -945,31 +1016,61 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
 static int predict_precomputed(gprc_ctx* c, FactorState& F, PredictWorkspace& ws, const double* weights,
                                const double* rowscale, const double* Ks, const double* kss, long m, double* mean,
                                double* var) {
-  GPRC_CHECK(ensure_inverse(c, F));
-  GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
-  double *dmean = nullptr, *dvar = nullptr, *stage = nullptr;
-  GPRC_CHECK(dmalloc(&dmean, (size_t)ws.mc));
-  GPRC_CHECK(dmalloc(&dvar, (size_t)ws.mc));
-  GPRC_CHECK(dmalloc(&stage, (size_t)F.n * std::min<long>(ws.mc, m)));
-  int rc = 0;
-  for (long c0 = 0; c0 < m && rc == 0; c0 += ws.mc) {
-    const long mcur = std::min(ws.mc, m - c0);
-    const long mpad = round_up(mcur, NB);
-    cudaMemcpyAsync(stage, Ks + c0 * F.n, sizeof(double) * F.n * mcur, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(ws.kss, kss + c0, sizeof(double) * mcur, cudaMemcpyHostToDevice, c->stream);
-    gemv_t_rect_kernel<<<(unsigned)((mcur + 7) / 8), 256, 0, c->stream>>>(stage, F.n, F.n, mcur, weights, dmean);
-    transpose_pad_kernel<<<dim3((unsigned)(F.n_pad / 32), (unsigned)(mpad / 32)), 256, 0, c->stream>>>(
-        stage, F.n, F.n, mcur, ws.Ks, ws.mc, F.n_pad, mpad, rowscale);
-    c->launches += 2;
-    if ((rc = variance_pass(c, F, ws, mpad, nullptr, 0))) break;
-    finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
-        nullptr, 0, 0, ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, nullptr, dvar);
-    c->launches++;
-    cudaMemcpyAsync(mean + c0, dmean, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(var + c0, dvar, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  // default: W = L^-1 once and one triangular GEMM per chunk; a forced GPRC_OPT_PREDICT_PATH of 2 / 4 takes the FP64 /
+  // INT8 substitution instead (tests drive the INT8 pass with arbitrary K, K_star through this)
+  int path = c->opt_predict_path;
+  if (path != 2 && path != 4) path = 1;
+  if (path == 1) GPRC_CHECK(ensure_inverse(c, F));
+  if (path == 4) {
+    GPRC_CHECK(oz_factor_digits_any(c, F));
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 8.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad));
+  } else {
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m));
   }
+  c->last_predict_path = path;
+  double *dmean = nullptr, *dvar = nullptr, *stage = nullptr;
+  int rc = 0;
+  do {
+    if ((rc = dmalloc(&dmean, (size_t)ws.mc))) break;
+    if ((rc = dmalloc(&dvar, (size_t)ws.mc))) break;
+    if ((rc = dmalloc(&stage, (size_t)F.n * std::min<long>(ws.mc, m)))) break;
+    for (long c0 = 0; c0 < m && rc == 0; c0 += ws.mc) {
+      const long mcur = std::min(ws.mc, m - c0);
+      const long mpad = round_up(mcur, NB);
+      cudaMemcpyAsync(stage, Ks + c0 * F.n, sizeof(double) * F.n * mcur, cudaMemcpyHostToDevice, c->stream);
+      cudaMemcpyAsync(ws.kss, kss + c0, sizeof(double) * mcur, cudaMemcpyHostToDevice, c->stream);
+      gemv_t_rect_kernel<<<(unsigned)((mcur + 7) / 8), 256, 0, c->stream>>>(stage, F.n, F.n, mcur, weights, dmean);
+      c->launches++;
+      int pass = path;
+      for (;;) {
+        transpose_pad_kernel<<<dim3((unsigned)(F.n_pad / 32), (unsigned)(mpad / 32)), 256, 0, c->stream>>>(
+            stage, F.n, F.n, mcur, ws.Ks, ws.mc, F.n_pad, mpad, rowscale);
+        c->launches++;
+        rc = pass == 4 ? variance_pass_ozaki(c, F, ws, mcur, mpad)
+             : pass == 2 ? variance_pass_trsm(c, F, ws, mpad)
+                         : variance_pass(c, F, ws, mpad, nullptr, 0);
+        if (rc || pass != 4) break;
+        cudaMemcpyAsync(c->h_info, ws.sched + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+          rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+          break;
+        }
+        const int flag = *reinterpret_cast<int*>(c->h_info);
+        if (flag & ~3) rc = set_error(-6, __FILE__, __LINE__, "INT8 substitution kernel: a pipeline barrier never completed");
+        if (rc || !flag) break;
+        pass = 2;  // v left its fixed-point range (K_star is not a covariance of this model): redo the chunk in FP64
+      }
+      if (rc) break;
+      finalize_predict_kernel<<<(unsigned)((mcur + 255) / 256), 256, 0, c->stream>>>(
+          nullptr, 0, 0, ws.pvar, ws.mc, (int)(F.n_pad / NB), ws.kss, mcur, nullptr, dvar);
+      c->launches++;
+      cudaMemcpyAsync(mean + c0, dmean, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(var + c0, dvar, sizeof(double) * mcur, cudaMemcpyDeviceToHost, c->stream);
+      cudaError_t e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) rc = set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+    }
+  } while (0);
   dfree(dmean);
   dfree(dvar);
   dfree(stage);
@@ -2085,6 +2186,49 @@ extern "C" int gprc_dev_dgemm(gprc_ctx* c, int transb, long M, long N, long K, d
   }
   DgemmPolicy<true> p{dA, lda, dB, ldb, dC, ldc, alpha, beta, (int)K, (int)(M / NB)};
   return launch_gemm(c, p, grid);
+}
+
+// Measured INT8 tensor-pipe rate (the roofline denominator of the INT8 variance pass, bench.py): a pure stream of
+// 128 x 256 x 32 tcgen05.mma kind::i8 from shared memory on every SM -- no feed, no drain -- repeated for about
+// `seconds` (a few milliseconds give the burst figure, seconds the figure under the board's power cap).
+extern "C" int gprc_dev_int8_rate(gprc_ctx* c, double seconds, double* tops, double* clk_per_mma) {
+  GPRC_ARG(c && tops && seconds > 0.0 && seconds <= 30.0);
+  DeviceGuard guard(c);
+  constexpr int N = 256, COUNT = 20000;
+  const int smem = 65536 + 8 * N * 32 + 1024;
+  GPRC_CUDA(cudaFuncSetAttribute(oz::mma_rate_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  long long* d = nullptr;
+  GPRC_CUDA(cudaMalloc(&d, 128));
+  GPRC_CUDA(cudaMemsetAsync(d, 0, 128, c->stream));
+  cudaEvent_t a = PhaseTimer::get_event(c), b = PhaseTimer::get_event(c);
+  auto launch = [&]() { oz::mma_rate_kernel<N, false><<<c->sm_count, 128, smem, c->stream>>>(COUNT, 1, 7, d); };
+  launch();  // warm-up
+  cudaStreamSynchronize(c->stream);
+  // one launch is COUNT * 128 clk ~ 1.3 ms: size the repetition count from a first timed launch
+  cudaEventRecord(a, c->stream);
+  launch();
+  cudaEventRecord(b, c->stream);
+  cudaStreamSynchronize(c->stream);
+  float ms1 = 0.f;
+  cudaEventElapsedTime(&ms1, a, b);
+  const int reps = std::max(1, (int)(seconds * 1e3 / std::max(ms1, 0.1f)));
+  cudaEventRecord(a, c->stream);
+  for (int r = 0; r < reps; ++r) launch();
+  cudaEventRecord(b, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  long long h[2] = {0, 0};
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  c->event_pool.push_back(a);
+  c->event_pool.push_back(b);
+  c->launches += reps + 2;
+  if (e != cudaSuccess) return set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e));
+  if (h[1] != 0) return set_error(-6, __FILE__, __LINE__, "INT8 rate probe: the MMA stream never completed");
+  *tops = 2.0 * 128.0 * N * 32.0 * (double)COUNT * (double)c->sm_count * (double)reps / ((double)ms * 1e-3) * 1e-12;
+  if (clk_per_mma) *clk_per_mma = (double)h[0] / (double)COUNT;
+  return 0;
 }
 
 extern "C" int gprc_dev_trtri(gprc_ctx* c, const double* dL, long n, long ld, const double* dinv, double* dW,

@@ -761,5 +761,287 @@ __global__ void __launch_bounds__(THREADS, 1) update128_kernel(const UpdateParam
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stacked-plane variant (round 2): the same 128 x 64 tile and the same S accumulators, but the products of one digit
+// plane of L with SEVERAL consecutive digit planes of V are ONE tcgen05.mma.
+//
+// The accumulators of orders o = a + b sit side by side in tensor memory (order o at columns 64 o), and the digit
+// planes of a V tile sit one after the other in shared memory (64 rows x 32 B each, 8-row groups 256 B apart), so
+//     [acc_a | acc_(a+1) | ... | acc_(a+nb-1)]  +=  A_a  x  [B_0 ; B_1 ; ... ; B_(nb-1)]^T
+// is a plain 128 x (64 nb) x 32 MMA: same D / B base addresses as the single products, N = 64 nb in the instruction
+// descriptor.  With both operands in shared memory a 128 x N x 32 INT8 MMA takes max(N / 2, 32 + N / 4) clk
+// (tools/oz_test rate): the 4 KB A tile is fetched once per MMA through the 128 B/clk operand port, which is what held
+// the 28 single products (N = 64: 48 clk against a 32 clk math floor) at 54 % of the pipe.  Stacked, S = 7 needs 11
+// MMAs per k-step (N = 256 / 192 / 128 / 64) and 912 clk instead of 1344, 98 % of the 896 clk math floor; the A tiles
+// cross the operand port 11 instead of 28 times.  Results are bit-identical to update_kernel (same integer sums).
+//
+// CL = 2: a cluster of two CTAs works on the SAME 64-point tile of V for two consecutive block rows of L
+// (rows 2 j and 2 j + 1 against k < 256 j).  Each CTA's producer fetches its own L digits and HALF of the V digits of
+// the k-step, multicast into both CTAs' shared memory: every V byte leaves L2 / HBM once per 256 rows instead of once
+// per 128.  Each CTA issues its own cta_group::1 MMAs into its own tensor memory; a ring slot is refilled once BOTH
+// CTAs' MMAs have read it (tcgen05.commit multicast onto both `empty` barriers, count 2).  The host then runs one small
+// FP64 step between the two diagonal solves of the pair (R[2j+1] -= L[2j+1, 2j] V[2j]).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset in every CTA of `mask`; each destination's mbarrier (same offset)
+// receives the byte count
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// the barrier at this offset in every CTA of `mask` arrives once the MMAs issued so far by this thread have completed
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+// planes of V multiplied with plane a of L: b = 0 .. S-1-a, in one MMA if <= 4 planes (N <= 256), else in two halves
+__host__ __device__ constexpr int stack_first(int S, int a) { return (S - a) <= 4 ? (S - a) : (S - a + 1) / 2; }
+__host__ __device__ constexpr int stack_mmas(int S) {
+  int n = 0;
+  for (int a = 0; a < S; ++a) n += (S - a) <= 4 ? 1 : 2;
+  return n;
+}
+
+// CL == 1: p.i = block row i (k < 128 i), grid = mpad / 64.
+// CL == 2: p.i = pair index j (block rows 2 j, 2 j + 1, k < 256 j), grid = 2 * (mpad / 64), launched with cluster
+// dimension (2, 1, 1).
+template <int S, int CL>
+__global__ void __launch_bounds__(THREADS, 1) update_stack_kernel(const UpdateParams p) {
+  static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
+  static_assert(S * BN <= TMEM_COLS, "accumulators must fit the tensor memory");
+  static_assert((S * B_TILE / CL) % 16 == 0, "bulk copies are multiples of 16 bytes");
+  using C = Cfg<S>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stg_all = reinterpret_cast<double*>(smem_raw + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + C::STAGES * C::STAGE_BYTES + DRAIN_STAGING_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tmem_full = empty + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int tc = blockIdx.x / CL;
+  const int brow = CL * p.i + (int)rank;       // this CTA's block row of L
+  const int KT = 4 * CL * p.i;                 // k-steps (the same for every CTA of the cluster)
+  constexpr int KT_CHUNK = C::KC / BK;
+  const int nchunks = (KT + KT_CHUNK - 1) / KT_CHUNK;
+  constexpr uint16_t ALL = (uint16_t)((1u << CL) - 1u);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), CL);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    mbar_init(smem_u32(tmem_empty), 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // barrier inits of every CTA are visible before any multicast copy / commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: own L digits; 1 / CL of the V digits of the k-step, multicast to the cluster =====
+    const int8_t* a_src = p.Ls + (long)brow * p.KB * (long)(S * A_TILE);
+    constexpr int VPART = S * B_TILE / CL;
+    const int8_t* b_src = p.Vs + (long)tc * p.KB * (long)(S * B_TILE) + (long)rank * VPART;
+    for (int kt = 0; kt < KT; ++kt) {
+      const int s = kt % C::STAGES;
+      if (kt >= C::STAGES) mbar_wait_guarded(smem_u32(empty + s), ((kt / C::STAGES) - 1) & 1, p.error, 16);
+      if (elect_one()) {
+        const uint32_t bar = smem_u32(full + s);
+        const uint32_t dst = smem_u32(smem_raw + s * C::STAGE_BYTES);
+        if (p.dbg & 2) {
+          mbar_arrive(bar);
+        } else {
+          mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+          bulk_g2s(dst, a_src + (long)kt * (S * A_TILE), S * A_TILE, bar);
+          if (CL == 1)
+            bulk_g2s(dst + S * A_TILE, b_src + (long)kt * (S * B_TILE), S * B_TILE, bar);
+          else
+            bulk_g2s_multicast(dst + S * A_TILE + rank * VPART, b_src + (long)kt * (S * B_TILE), VPART, bar, ALL);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      constexpr int NMMA = stack_mmas(S), WAITPOS = NMMA / 2 - 1;
+      int kt = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        if (c > 0) {
+          mbar_wait_guarded(smem_u32(tmem_empty), (c - 1) & 1, p.error, 32);
+          tc_fence_after();
+        }
+        const int kt_end = min(KT, (c + 1) * KT_CHUNK);
+        mbar_wait_guarded(smem_u32(full + kt % C::STAGES), (kt / C::STAGES) & 1, p.error, 64);
+        tc_fence_after();
+        for (bool first = true; kt < kt_end; ++kt, first = false) {
+          const int s = kt % C::STAGES;
+          if (p.dbg & 1) {
+            if (kt + 1 < kt_end) mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
+            if (CL == 1) mbar_arrive(smem_u32(empty + s));
+            else tc_commit_multicast(smem_u32(empty + s), ALL);
+          } else {
+            const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES);
+            const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + S * A_TILE, 128, 256);
+            int issued = 0;
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              const int n1 = stack_first(S, a), n2 = (S - a) - n1;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int b0 = h ? n1 : 0, nb = h ? n2 : n1;
+                if (nb == 0) continue;
+                if (issued == WAITPOS && kt + 1 < kt_end) {
+                  // the wait for the NEXT stage sits in the middle of this stage's MMAs: the tensor pipe has queued
+                  // work while the issuing lane pays the try_wait / fence latency
+                  mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
+                  tc_fence_after();
+                }
+                // accumulator a + b is first written in this chunk by plane a = 0 at the chunk's first k-step
+                mma_i8(tmem_base + (uint32_t)((a + b0) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                       bd0 + (uint64_t)(b0 * (B_TILE >> 4)), instr_desc_i8(BM, BN * nb), (!first || a > 0) ? 1u : 0u);
+                ++issued;
+              }
+            }
+            if (CL == 1) tc_commit(smem_u32(empty + s));
+            else tc_commit_multicast(smem_u32(empty + s), ALL);  // the slot is free once every CTA's MMAs have read it
+          }
+          if (kt + 1 == kt_end) tc_commit(smem_u32(tmem_full));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== drain (as update_kernel): TMEM -> registers -> transpose through shared memory -> R in place =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const double sr = p.scale_row[(long)brow * BM + row];
+    const double* sc = p.scale_col + (long)tc * BN;
+    double* stg = stg_all + q * (32 * 9);
+    double* cbase = p.T + (long)tc * BN + ((long)brow * BM + q * 32 + (lane >> 3)) * p.ldt + (lane & 7);
+    {
+      const double* prow = p.T + (long)tc * BN + ((long)brow * BM + row) * p.ldt;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prefetch_l2(prow + j * 16);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait_guarded(smem_u32(tmem_full), c & 1, p.error, 128);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < BN / 8; ++g) {
+        int32_t acc[S][8];
+#pragma unroll
+        for (int o = 0; o < S; ++o) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + g * 8), acc[o]);
+        double cur[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] = cbase[(long)(it * 4) * p.ldt + g * 8];
+        double scv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) scv[j] = __ldg(sc + g * 8 + j);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          double h = (double)acc[S - 1][j];
+#pragma unroll
+          for (int o = S - 2; o >= 0; --o) h = fma(h, 0.00390625, (double)acc[o][j]);
+          stg[lane * 9 + j] = (sr * scv[j]) * h;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cur[it] -= stg[(it * 4 + (lane >> 3)) * 9 + (lane & 7)];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) cbase[(long)(it * 4) * p.ldt + g * 8] = cur[it];
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into its shared memory / barriers
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// tensor-pipe rate probe (bench.py's measured INT8 peak, tools/oz_test rate): one CTA per SM issues `count` int8 MMAs of
+// shape 128 x N x 32 from (uninitialised) shared memory, rotating over `rot` accumulators and `nsrc` operand tiles;
+// out[0] = clocks CTA 0 took
+template <int N, bool TS>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int count, int rot, int nsrc, long long* out) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = slot;
+  if (warp == 0 && elect_one()) {
+    const uint32_t idesc = instr_desc_i8(128, N);
+    const uint32_t s0 = smem_u32(sm);
+    const long long t0 = clock64();
+    // 8 products per trip, descriptors and accumulator addresses precomputed: the loop must not be issue-bound
+    uint64_t ad[8], bd[8];
+    uint32_t dd[8], at[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      ad[u] = smem_desc(s0 + (u % nsrc) * 4096, 128, 256);
+      bd[u] = smem_desc(s0 + 65536 + (u % nsrc) * (N * 32), 128, 256);
+      dd[u] = tb + (u % rot) * N;
+      at[u] = tb + 448 + (u % nsrc) * 8;
+    }
+    for (int it = 0; it < count; it += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (TS) mma_i8_ts(dd[u], at[u], bd[u], idesc, 1u);
+        else mma_i8(dd[u], ad[u], bd[u], idesc, 1u);
+      }
+    }
+    tc_commit(smem_u32(&bar));
+    mbar_wait_guarded(smem_u32(&bar), 0, (int*)out + 8, 1);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tb, 512);
+  }
+}
+
+
 }  // namespace oz
 }  // namespace gprc

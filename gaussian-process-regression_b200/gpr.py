@@ -158,6 +158,10 @@ class GPR:
             raise ValueError("is.numeric(X_star), length(X_star) %% nrow(self$X) == 0 are not all TRUE")
         if X_star.ndim < 2:
             X_star = X_star.reshape(-1, D).T  # dim(X_star) <- c(D, length / D)  (column-major fill)
+        elif X_star.ndim != 2 or X_star.shape[0] != D:
+            # a matrix with the wrong number of rows passes the length check of R/GPRclass.R:156 and then fails inside
+            # covariance_matrix ("non-conformable arrays"): the library must never read d * m doubles from such a buffer
+            raise ValueError("non-conformable arrays: nrow(X_star) = %d, nrow(self$X) = %d" % (X_star.shape[0], D))
         m = X_star.shape[1]
         lib, h = self._ctx.lib, self._handle
         spec = kernel_spec_of(self._k)

@@ -117,6 +117,8 @@ int gprc_ctx_mark(gprc_ctx* ctx, int slot /* 0..7 */);
 int gprc_ctx_elapsed_ms(gprc_ctx* ctx, int slot_start, int slot_stop, double* ms);
 /* variance-pass path (1..4, see GPRC_OPT_PREDICT_PATH) the most recent predict on this context resolved to; 0 = none yet */
 int gprc_ctx_last_predict_path(gprc_ctx* ctx);
+/* chunks of test points that predict was cut into (each chunk reads the factor once: bench.py's algorithmic bytes) */
+long gprc_ctx_last_predict_chunks(gprc_ctx* ctx);
 const char* gprc_last_error(void);
 int gprc_version(void);
 
@@ -265,6 +267,11 @@ int gprc_dev_potrf(gprc_ctx* ctx, double* dA, long n, long ld, double* dinv, lon
  * transb = 0: B is K x N col-major.  M, N multiples of 128, K multiple of 16. */
 int gprc_dev_dgemm(gprc_ctx* ctx, int transb, long M, long N, long K, double alpha, const double* dA, long lda,
                    const double* dB, long ldb, double beta, double* dC, long ldc);
+/* Measured INT8 tensor-pipe rate -- the roofline denominator of predict path 4 (bench.py `roofline.peak`): a pure stream
+   of 128 x 256 x 32 tcgen05.mma kind::i8 on every SM for about `seconds` (milliseconds: burst; seconds: under the power
+   cap).  tops = 1e-12 x INT8 operations per second (2 per multiply-add); clk_per_mma from CTA 0's clock counter (math
+   floor: 128).  No reference counterpart (measurement only). */
+int gprc_dev_int8_rate(gprc_ctx* ctx, double seconds, double* tops, double* clk_per_mma);
 /* W = L^-1 for a lower-triangular n x n device matrix whose diagonal blocks' inverses are in dinv. dscratch: n x n. */
 int gprc_dev_trtri(gprc_ctx* ctx, const double* dL, long n, long ld, const double* dinv, double* dW,
                    double* dscratch);

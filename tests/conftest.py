@@ -15,14 +15,15 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # `-m "not gpu"` (the CPU tier) also selects gpu_next tests: they need a device, so they are skipped without one
+    # `-m "not gpu"` (the CPU tier) also selects gpu_next tests, and a plain `pytest tests` selects the gpu ones: both
+    # need a device, so they are skipped (not failed) without one
     import shutil
     has_gpu = shutil.which("nvidia-smi") is not None and os.system("nvidia-smi -L > /dev/null 2>&1") == 0
     if has_gpu:
         return
-    skip = pytest.mark.skip(reason="gpu_next: needs a CUDA device")
+    skip = pytest.mark.skip(reason="needs a CUDA device")
     for item in items:
-        if "gpu_next" in item.keywords:
+        if "gpu_next" in item.keywords or "gpu" in item.keywords:
             item.add_marker(skip)
 
 

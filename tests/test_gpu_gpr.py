@@ -311,3 +311,27 @@ def test_gpu_path_matches_committed_golden_vectors(gprc, tag):
     assert_mean_var(got, ref, np.abs(kss))
     assert abs(g.logp[0, 0] - float(GOLD[tag + "_logp"])) <= LOGP_RTOL * abs(float(GOLD[tag + "_logp"]))
     np.testing.assert_allclose(g.alpha, GOLD[tag + "_alpha"], rtol=0, atol=1e-8 * np.max(np.abs(GOLD[tag + "_alpha"])))
+
+
+def test_long_predict_polls_the_interrupt_callback(gprc, ctx):
+    """gprc_ctx_set_interrupt: polled between chunks of test points; a non-zero answer abandons the call
+    with status -8 and leaves the context usable."""
+    import ctypes as C
+    rng = np.random.default_rng(39)
+    n, m = 300, (1 << 20) + 5000          # the chunk capacity is capped at 2^20 test points: two chunks
+    X = rng.uniform(-6, 6, (1, n))
+    y = 0.1 * X[0] ** 3 + rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-6, 6, (1, m))
+    g = gprc.GPR(X, y, 0.01, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    calls = []
+    cb_type = C.CFUNCTYPE(C.c_int, C.c_void_p)
+    cb = cb_type(lambda user: (calls.append(1), 1)[1])
+    gprc._lib.check(ctx.lib.gprc_ctx_set_interrupt(ctx.handle, cb, None))
+    try:
+        with pytest.raises(gprc._lib.GprcError, match="interrupted"):
+            g.predict(Xs)
+    finally:
+        gprc._lib.check(ctx.lib.gprc_ctx_set_interrupt(ctx.handle, C.cast(None, cb_type), None))
+    assert len(calls) == 1
+    out = g.predict(Xs[:, :1000])         # the context and the model still work
+    assert np.all(np.isfinite(out))

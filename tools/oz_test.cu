@@ -1,7 +1,7 @@
 // oz_test.cu -- standalone check of the INT8 (tcgen05) substitution update of csrc/ozaki.cuh against (a) a host
 // emulation of exactly the same digit arithmetic and (b) the plain FP64 product; plus a timing mode.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/oz_test tools/oz_test.cu
-//   tools/oz_test check|time <S> <n> <mc> <i> [ts 0 [dbg]]   (ts = 1: A operand from tensor memory, 2: wide 128 x 128 kernel, 3: CTA-pair kernel, i = pair index)   tools/oz_test digits
+//   tools/oz_test check|time <S> <n> <mc> <i> [ts 0 [dbg]]   (ts = 1: A operand from tensor memory, 2: wide 128 x 128 kernel, 4: stacked-plane kernel, 5: stacked-plane kernel on clusters of 2 with V multicast, i = pair index)   tools/oz_test digits
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -10,7 +10,6 @@
 #include <algorithm>
 
 #include "../gaussian-process-regression_b200/csrc/ozaki.cuh"
-#include "../gaussian-process-regression_b200/csrc/ozaki_pair.cuh"  // not yet run on hardware (mode 3)
 
 namespace gprc {
 thread_local std::string g_last_error;
@@ -37,7 +36,7 @@ __global__ void clock_probe(long long* out) {
   out[1] = (long long)(t1 - t0);
 }
 
-template <int S, bool TS, bool WIDE = false, bool PAIR = false>
+template <int S, bool TS, bool WIDE = false, bool PAIR = false, bool STACK = false>
 static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, int dbg) {
   const long n_pad = n, KB = n_pad / 32;
   std::mt19937_64 rng(12345);
@@ -75,7 +74,7 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   oz::colscale_kernel<<<(unsigned)((mc + 255) / 256), 256>>>(dkss, mc, mc, decol, dsc);
   const int rows_done = PAIR ? 2 * i : i;  // block rows of V that exist before the update under test
   for (int b = 0; b < rows_done; ++b) {
-    if constexpr (WIDE || PAIR) oz::split_v128_kernel<S><<<dim3((unsigned)(mc / 128), 4), 256>>>(dT, mc, b, decol, dVs, (int)KB, derr);
+    if constexpr (WIDE) oz::split_v128_kernel<S><<<dim3((unsigned)(mc / 128), 4), 256>>>(dT, mc, b, decol, dVs, (int)KB, derr);
     else oz::split_v_kernel<S><<<dim3((unsigned)(mc / 64), 4), 128>>>(dT, mc, b, decol, dVs, (int)KB, derr);
   }
   CK(cudaDeviceSynchronize());
@@ -84,14 +83,30 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
   printf("split done, overflow flag = %d\n", herr);
 
   auto launch = [&](const oz::UpdateParams& q) {
-    if constexpr (PAIR) oz::update_pair_kernel<S><<<(unsigned)(2 * (mc / 128)), oz::THREADS, oz::CfgPair<S>::SMEM_BYTES>>>(q);
+    if constexpr (PAIR) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(2 * (mc / 64)));
+      cfg.blockDim = dim3(oz::THREADS);
+      cfg.dynamicSmemBytes = oz::Cfg<S>::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, oz::update_stack_kernel<S, 2>, q);
+    } else if constexpr (STACK) oz::update_stack_kernel<S, 1><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(q);
     else if constexpr (WIDE) oz::update128_kernel<S><<<(unsigned)(mc / 128), oz::THREADS, oz::Cfg2<S>::SMEM_BYTES>>>(q);
     else oz::update_kernel<S, TS><<<(unsigned)(mc / 64), oz::THREADS, oz::Cfg<S>::SMEM_BYTES>>>(q);
   };
   if constexpr (PAIR) {
-    CK(cudaFuncSetAttribute(oz::update_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::CfgPair<S>::SMEM_BYTES));
-    printf("pair kernel: clusters of 2 CTAs, 256 x 128 tiles (block rows %d and %d against k < %d), ring %d B, stages %d / %d\n",
-           2 * i, 2 * i + 1, 256 * i, oz::CfgPair<S>::RING, oz::CfgPair<S>::STAGES0, oz::CfgPair<S>::STAGES1);
+    CK(cudaFuncSetAttribute(oz::update_stack_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    printf("stacked kernel on clusters of 2: block rows %d and %d against k < %d, V digits multicast; %d MMAs per k-step\n",
+           2 * i, 2 * i + 1, 256 * i, oz::stack_mmas(S));
+  } else if constexpr (STACK) {
+    CK(cudaFuncSetAttribute(oz::update_stack_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<S>::SMEM_BYTES));
+    printf("stacked kernel: %d MMAs per k-step\n", oz::stack_mmas(S));
   } else if constexpr (WIDE) {
     CK(cudaFuncSetAttribute(oz::update128_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg2<S>::SMEM_BYTES));
     printf("wide kernel: 128 x 128 tiles, two order passes, ring %d B, stages %d / %d\n", oz::Cfg2<S>::RING,
@@ -139,9 +154,11 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     long long hclk[2];
     CK(cudaMemcpy(hclk, dclk, 16, cudaMemcpyDeviceToHost));
     const double mhz = (double)hclk[0] / (double)hclk[1] * 1e3;
+    const long ctas = PAIR ? 2 * (mc / 64) : (WIDE ? mc / 128 : mc / 64);
     printf("update_kernel<%d,%s%s> dbg=%d: %.3f ms  -> %.1f TFLOP/s FP64-equivalent, %.2f POP/s int8 (%d products); SM clock %.0f MHz, "
-           "%.0f clk per k-step\n", S, TS ? "TS" : "SS", WIDE ? " wide" : "", dbg, ms, flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
-           ms * 1e-3 * mhz * 1e6 / ((PAIR ? 8.0 : 4.0) * i) / ((mc / (WIDE ? 128 : (PAIR ? 64 : 64)) + 147) / 148));
+           "%.0f clk per k-step and CTA\n", S, TS ? "TS" : "SS", PAIR ? " stack pair" : (STACK ? " stack" : (WIDE ? " wide" : "")), dbg, ms,
+           flops / ms * 1e-9, flops * (S * (S + 1) / 2) / ms * 1e-12, S * (S + 1) / 2, mhz,
+           ms * 1e-3 * mhz * 1e6 / ((PAIR ? 8.0 : 4.0) * i) / ((ctas + 147) / 148));
     return 0;
   }
 
@@ -215,61 +232,9 @@ static int run(bool timing, long n, long mc, int i, uint32_t lbo, uint32_t sbo, 
     }
   }
   printf("RESULT S=%d %s%s i=%d: err flag %d, vs digit emulation max %.3e (%ld bad of %ld), vs fp64 max %.3e (|ref| max %.3e)%s\n",
-         S, TS ? "TS" : "SS", PAIR ? " pair" : (WIDE ? " wide" : ""), i, herr, max_emul, bad, (long)nrows * mc, max_fp64, max_ref,
+         S, TS ? "TS" : "SS", PAIR ? " stack pair" : (STACK ? " stack" : (WIDE ? " wide" : "")), i, herr, max_emul, bad, (long)nrows * mc, max_fp64, max_ref,
          bad == 0 ? "  OK" : "  FAIL");
   return bad == 0 ? 0 : 1;
-}
-
-// tensor-pipe rate probe: one CTA per SM issues `count` int8 MMAs of shape 128 x N x 32 from (uninitialised) shared
-// memory, rotating over `rot` accumulators and `nsrc` operand tiles; reports clocks per MMA
-template <int N, bool TS>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int count, int rot, int nsrc, long long* out) {
-  extern __shared__ __align__(128) unsigned char sm[];
-  __shared__ uint64_t bar;
-  __shared__ uint32_t slot;
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bar), 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) oz::tmem_alloc(smem_u32(&slot), 512);
-  oz::tc_fence_before();
-  __syncthreads();
-  oz::tc_fence_after();
-  const uint32_t tb = slot;
-  if (warp == 0 && oz::elect_one()) {
-    const uint32_t idesc = oz::instr_desc_i8(128, N);
-    const uint32_t s0 = smem_u32(sm);
-    const long long t0 = clock64();
-    // 8 products per trip, descriptors and accumulator addresses precomputed: the loop must not be issue-bound
-    uint64_t ad[8], bd[8];
-    uint32_t dd[8], at[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      ad[u] = oz::smem_desc(s0 + (u % nsrc) * 4096, 128, 256);
-      bd[u] = oz::smem_desc(s0 + 65536 + (u % nsrc) * (N * 32), 128, 256);
-      dd[u] = tb + (u % rot) * N;
-      at[u] = tb + 448 + (u % nsrc) * 8;
-    }
-    for (int it = 0; it < count; it += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (TS) oz::mma_i8_ts(dd[u], at[u], bd[u], idesc, 1u);
-        else oz::mma_i8(dd[u], ad[u], bd[u], idesc, 1u);
-      }
-    }
-    oz::tc_commit(smem_u32(&bar));
-    oz::mbar_wait_guarded(smem_u32(&bar), 0, (int*)out + 8, 1);
-    const long long t1 = clock64();
-    if (blockIdx.x == 0) out[0] = t1 - t0;
-  }
-  oz::tc_fence_before();
-  __syncthreads();
-  oz::tc_fence_after();
-  if (warp == 0) {
-    __syncwarp();
-    oz::tmem_dealloc(tb, 512);
-  }
 }
 
 template <int N, bool TS>
@@ -278,8 +243,8 @@ static void mma_rate(int rot, int nsrc) {
   cudaMalloc(&d, 128);
   cudaMemset(d, 0, 128);
   const int smem = 65536 + 8 * N * 32 + 1024, count = 20000;
-  cudaFuncSetAttribute(mma_rate_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int w = 0; w < 3; ++w) mma_rate_kernel<N, TS><<<148, 128, smem>>>(count, rot, nsrc, d);
+  cudaFuncSetAttribute(oz::mma_rate_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int w = 0; w < 3; ++w) oz::mma_rate_kernel<N, TS><<<148, 128, smem>>>(count, rot, nsrc, d);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
@@ -369,20 +334,25 @@ int main(int argc, char** argv) {
   const int i = atoi(argv[5]);
   const uint32_t lbo = argc > 7 ? (uint32_t)atoi(argv[6]) : 0u, sbo = 0u;  // argv[6] = 1 selects the TS kernel
   const int dbg = argc > 8 ? atoi(argv[8]) : 0;
-  if (n % 128 || mc % 128 || i < 1 || i >= n / 128 || (argc > 7 && atoi(argv[6]) == 3 && 2 * i + 1 >= n / 128)) {
+  if (n % 128 || mc % 128 || i < 1 || i >= n / 128 || (argc > 7 && atoi(argv[6]) == 5 && 2 * i + 1 >= n / 128)) {
     printf("bad sizes\n");
     return 64;
   }
+#define OZ_DISPATCH(SS)                                                                          \
+  (lbo == 5   ? run<SS, false, false, true, true>(timing, n, mc, i, lbo, sbo, dbg)               \
+   : lbo == 4 ? run<SS, false, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)              \
+   : lbo == 2 ? run<SS, false, true>(timing, n, mc, i, lbo, sbo, dbg)                            \
+   : lbo == 1 ? run<SS, true>(timing, n, mc, i, lbo, sbo, dbg)                                   \
+              : run<SS, false>(timing, n, mc, i, lbo, sbo, dbg))
   switch (S) {
     case 1: return (lbo == 1 ? run<1, true>(timing, n, mc, i, lbo, sbo, dbg) : run<1, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 2: return (lbo == 1 ? run<2, true>(timing, n, mc, i, lbo, sbo, dbg) : run<2, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 6: return (lbo == 3 ? run<6, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
-                             : lbo == 2 ? run<6, false, true>(timing, n, mc, i, lbo, sbo, dbg)
-                             : lbo == 1 ? run<6, true>(timing, n, mc, i, lbo, sbo, dbg) : run<6, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 7: return (lbo == 3 ? run<7, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
-                             : lbo == 2 ? run<7, false, true>(timing, n, mc, i, lbo, sbo, dbg)
-                             : lbo == 1 ? run<7, true>(timing, n, mc, i, lbo, sbo, dbg) : run<7, false>(timing, n, mc, i, lbo, sbo, dbg));
-    case 8: return (lbo == 2 ? run<8, false, true>(timing, n, mc, i, lbo, sbo, dbg) : run<8, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 2: return (lbo == 4 ? run<2, false, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                             : lbo == 1 ? run<2, true>(timing, n, mc, i, lbo, sbo, dbg) : run<2, false>(timing, n, mc, i, lbo, sbo, dbg));
+    case 6: return OZ_DISPATCH(6);
+    case 7: return OZ_DISPATCH(7);
+    case 8: return (lbo == 5   ? run<8, false, false, true, true>(timing, n, mc, i, lbo, sbo, dbg)
+                    : lbo == 4 ? run<8, false, false, false, true>(timing, n, mc, i, lbo, sbo, dbg)
+                    : lbo == 2 ? run<8, false, true>(timing, n, mc, i, lbo, sbo, dbg) : run<8, false>(timing, n, mc, i, lbo, sbo, dbg));
   }
   printf("S must be 1, 2, 6, 7 or 8\n");
   return 64;
