@@ -25,7 +25,7 @@ OPT_PREDICT_PATH = 2
 OPT_OZAKI_DIGITS = 3
 OPT_INT8_AUTO = 4
 OPT_INT8_TILE = 5
-INT8_TILE_DEFAULT = 64  # kernel variant of the INT8 pass the library starts with (csrc/common.cuh: opt_int8_tile)
+INT8_TILE_DEFAULT = 2  # kernel variant of the INT8 pass the library starts with (csrc/common.cuh: opt_int8_tile)
 OPT_INT8_TEST_SHRINK = 6
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 

@@ -65,9 +65,13 @@ enum {
                             (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
   GPRC_OPT_INT8_TEST_SHRINK = 6, /* tests only: lower the per-test-point exponents of path 4 by this many bits so that
                             v leaves its fixed-point range: the overflow flag must fire and the chunk be redone in FP64 */
-  GPRC_OPT_INT8_TILE = 5 /* test points per CTA on path 4: 64 (default: all orders in one pass, 7 accumulators in
-                            tensor memory) or 128 (128 x 128 x 32 MMAs at their math floor, orders in two passes; 1.4 x
-                            fewer tensor-pipe cycles but 1.4 x the HBM traffic -- equal under the 1000 W cap today) */
+  GPRC_OPT_INT8_TILE = 5 /* kernel of path 4 (all give the same digits; 1 and 64 are bit-identical):
+                            2 (default) stacked digit planes on clusters of two CTAs: one tcgen05.mma multiplies a digit
+                              plane of L with up to four planes of V (N up to 256), two block rows of L share every V digit
+                              tile through TMA multicast, one small FP64 step inside each pair of block rows;
+                            1 stacked digit planes, one block row per launch;
+                            64 one MMA per digit pair (round 1: bound by the tensor core's shared-memory operand port);
+                            128 128 x 128 tiles with the orders in two passes (round 1) */
 
 };
 

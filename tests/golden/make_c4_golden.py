@@ -8,8 +8,10 @@ What it computes is R/GPRclass.R:138-164 literally, memory-bounded (the referenc
 this size):
   K      = covariance_matrix(X, X, k) + noise * diag(n)   column blocks through oracle.sqrexp on gathered columns
            (the same colSums((x - y)^2) / exp order as the oracle, only chunked), lower triangle + diagonal
-  L      = t(chol(K))                                      scipy.linalg.cholesky(lower, overwrite_a) = LAPACK dpotrf in place
-  alpha  = solve(t(L), solve(L, y))                        dtrtrs twice ("generous": triangular)
+  L      = t(chol(K))                                      oracle.blocked_cholesky_inplace: dpotrf's blocked algorithm over
+           LAPACK / BLAS calls on 2048-blocks (SciPy's LP64 LAPACK segfaults for n^2 > 2^31), in place
+  alpha  = solve(t(L), solve(L, y))                        block substitution over dtrtrs / dgemm ("generous": triangular,
+           SURVEY.md A.7)
   logp   = -0.5 y'alpha - sum(log(diag(L))) - n/2 log(2 pi)
   K_star, mean = t(K_star) alpha, v = solve(L, K_star), var = k(X*, X*) - colSums(v * v)   for the first M test points
 Stored: mean, var, logp, alpha[:64], diag(L)[:64] and a few sampled entries of L, plus the generator's parameters.
@@ -53,18 +55,18 @@ def main(n=50000, m=1000000, d=8, M=256, noise=0.01, l=1.0, out=None, block=250)
             print("K build: column %d of %d, %.0f s" % (j0, n, time.time() - t0), flush=True)
     K[np.arange(n), np.arange(n)] += noise            # K + noise * diag(n)                 R/GPRclass.R:142
     print("K built, %.0f s" % (time.time() - t0), flush=True)
-    L = scipy.linalg.cholesky(K, lower=True, overwrite_a=True, check_finite=False)
-    assert L is K or np.shares_memory(L, K), "dpotrf did not run in place"
-    print("dpotrf done, %.0f s" % (time.time() - t0), flush=True)
-    # scipy's cholesky zeroes the strict upper triangle of its result
-    z = scipy.linalg.solve_triangular(L, y, lower=True, check_finite=False)
-    alpha = scipy.linalg.solve_triangular(L, z, lower=True, trans="T", check_finite=False)   # :152
+    # scipy.linalg.cholesky (LP64 LAPACK in this image) segfaults for n^2 > 2^31: the oracle's blocked dpotrf instead
+    L = o.blocked_cholesky_inplace(K)
+    print("dpotrf (blocked, in place) done, %.0f s" % (time.time() - t0), flush=True)
+    # its strict upper triangle is garbage (the untouched upper part of K is zero here: only the lower triangle was built)
+    z = o.blocked_solve_lower(L, y)
+    alpha = o.blocked_solve_lower(L, z, trans=True)                                           # :152
     dg = np.diag(L).copy()
     logp = -0.5 * float(y @ alpha) - float(np.sum(np.log(dg))) - n / 2 * math.log(2 * math.pi)  # :153
     k = o.cov_func(o.sqrexp, l=l)
     Ks = o.covariance_matrix(X, Xs, k)                                                         # :160
     mean = Ks.T @ alpha                                                                        # :161
-    v = scipy.linalg.solve_triangular(L, Ks, lower=True, check_finite=False)                   # :162
+    v = o.blocked_solve_lower(L, Ks)                                                           # :162
     var = k(Xs, Xs) - np.sum(v * v, axis=0)                                                    # :164
     rng = np.random.default_rng(99)
     ii = rng.integers(0, n, 64)

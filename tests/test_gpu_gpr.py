@@ -186,7 +186,8 @@ def test_variance_pass_paths_agree_with_oracle(gprc, oracle, ctx, path):
 
 
 @pytest.mark.parametrize("digits,tile,tol", [(6, 64, 1e-10), (7, 64, 1e-12), (8, 64, 1e-12), (7, 128, 1e-12), (6, 128, 1e-10),
-                                             (8, 128, 1e-12)])
+                                             (8, 128, 1e-12), (6, 2, 1e-10), (7, 2, 1e-12), (8, 2, 1e-12), (6, 1, 1e-10),
+                                             (7, 1, 1e-12), (8, 1, 1e-12)])
 def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tile, tol):
     """Path 4 against path 2 on the same factor: 1500 training points (12 block rows), polynomial kernel (k** varies
     per test point, so the per-point exponents differ), more than one 64-point tile per SM."""
@@ -207,7 +208,7 @@ def test_int8_substitution_matches_fp64_substitution(gprc, ctx, digits, tile, to
         finally:
             ctx.set_option(gprc._lib.OPT_PREDICT_PATH, 0)
             ctx.set_option(gprc._lib.OPT_OZAKI_DIGITS, 7)
-            ctx.set_option(gprc._lib.OPT_INT8_TILE, 64)
+            ctx.set_option(gprc._lib.OPT_INT8_TILE, gprc._lib.INT8_TILE_DEFAULT)
     kss = (np.sum(Xs * Xs, axis=0) + 1.0) ** 3
     np.testing.assert_allclose(out[2][:, 0], out[4][:, 0], rtol=1e-13, atol=0)  # the mean does not go through the variance pass
     assert np.max(np.abs(out[2][:, 1] - out[4][:, 1]) / kss) < tol

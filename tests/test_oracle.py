@@ -70,17 +70,43 @@ def test_gpc_inequalities_test_gpc_R():
 
 
 def test_fit_model_selection_test_fit_R():
-    # tests/testthat/test-fit.R.  The restatement reproduces the first three outcomes; for Y4-Y6 it selects
-    # "polynomial" (the kernels have no signal-variance parameter, so a degree-2 polynomial explains amplitude-5 data
-    # better than sqrexp with unit variance).  Without R this cannot be checked against the reference itself: recorded
-    # as a regression value and flagged in DESIGN.md.
-    X = np.arange(0, 1.1001, 0.1).reshape(1, -1)
-    x = X[0]
-    names = ["linear", "constant", "polynomial", "sqrexp", "gammaexp", "rationalquadratic"]
-    Ys = [3 * x, np.full(12, 5.0), 3 * x ** 2 - 2 * x, 5 * np.exp(-x ** 2), 5 * np.exp(-x ** 5), 5 / (1 + x ** 2)]
-    got = [o.fit(X, Y, 0.05, names)["cov"] for Y in Ys]
-    assert got[:3] == ["linear", "constant", "polynomial"]
-    assert got[3:] == ["polynomial", "polynomial", "polynomial"]
+    """tests/testthat/test-fit.R:12-17.  Outcomes 1-3 (linear, constant, polynomial) are reproduced.  For Y4-Y6 the
+    reference's own expectation (sqrexp / gammaexp / rationalquadratic) is unattainable for ANY faithful implementation
+    of R/fit.R, R included: the kernels have unit prior variance and the targets amplitude 5, so even the global maximum
+    of the expected family's log marginal likelihood lies > 7 below the polynomial family's score -- shown here on a
+    parameter grid and, independently of NumPy / LAPACK / the oracle's dens(), in 40-digit arithmetic
+    (tools/test_fit_R_study.py, profiles/r2_test_fit_R_study.md).  What is asserted is that property, not an outcome."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "test_fit_R_study", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                                         "test_fit_R_study.py"))
+    study = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(study)
+    X, Ys = study.targets()
+    names = study.NAMES
+    res = [o.fit(X, Y, 0.05, names) for Y in Ys]
+    assert [r["cov"] for r in res[:3]] == ["linear", "constant", "polynomial"]          # test-fit.R:12-14 hold
+    for t in (3, 4, 5):                                                                   # test-fit.R:15-17
+        expected = study.EXPECTED[t]
+        poly = dict(zip(names, res[t]["score"]))["polynomial"]
+        # (a) the polynomial score is a correctly evaluated likelihood (40 digits, independent code)
+        assert res[t]["cov"] == "polynomial"
+        assert abs(study.mp_dens(X[0], Ys[t], 0.05, "polynomial", res[t]["par"]) - poly) < 1e-10
+        # (b) no parameter of the expected family comes near it: coarse global grid + the optimiser's own result
+        best = dict(zip(names, res[t]["score"]))[expected]
+        if expected == "sqrexp":
+            grid = [[l] for l in np.linspace(0.05, 10, 400)]
+        else:
+            ax = np.exp(np.linspace(math.log(0.05), math.log(100), 40))
+            grid = [[a, b] for a in ax for b in ax if not (expected == "gammaexp" and b > 2.0)]
+        for par in grid:
+            try:
+                best = max(best, o.dens(X, Ys[t], 0.05, expected, par, minors="cholesky"))
+            except o.OptimError:
+                pass
+        assert best < poly - 7.0, (expected, best, poly)
+        mid = grid[len(grid) // 2]   # and the oracle's dens() of the expected family agrees with the 40-digit evaluation
+        assert abs(study.mp_dens(X[0], Ys[t], 0.05, expected, mid) - o.dens(X, Ys[t], 0.05, expected, mid, minors="cholesky")) < 1e-9
 
 
 def test_r_optimisers_on_textbook_functions():
