@@ -30,6 +30,7 @@ GPC <- R6::R6Class("GPC",
     },
     predict_class = function(X_star) {
       if (!is.matrix(X_star)) dim(X_star) <- c(1, length(X_star))
+      if (nrow(X_star) != nrow(private$.X)) stop("non-conformable arrays")   # as covariance_matrix would (R/GPRclass.R:356)
       storage.mode(X_star) <- "double"
       spec <- .gprc_spec(private$.k)
       # built-in kernels: latent prediction and the integrate() loop in one device call (dqagi port, same tolerances)

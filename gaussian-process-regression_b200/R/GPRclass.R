@@ -37,6 +37,9 @@ GPR <- R6::R6Class("GPR",
     predict = function(X_star, pointwise_var = TRUE) {
       stopifnot(is.numeric(X_star), length(X_star) %% nrow(private$.X) == 0)
       if (is.null(dim(X_star))) dim(X_star) <- c(nrow(private$.X), length(X_star) / nrow(private$.X))
+      # a matrix with the wrong number of rows passes the length check above; the reference then fails inside
+      # covariance_matrix (R/GPRclass.R:356) -- fail here, before the library reads nrow(X) * m doubles
+      if (nrow(X_star) != nrow(private$.X)) stop("non-conformable arrays")
       storage.mode(X_star) <- "double"
       spec <- .gprc_spec(private$.k)
       if (pointwise_var) {

@@ -105,11 +105,15 @@ SIGNATURES = {
     "gprc_logistic_gaussian": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, c_int_p]),
     "gprc_gpc_get": (C.c_int, [_P, C.c_int, c_double_p]),
     "gprc_gpc_n": (C.c_long, [_P]),
+    "gprc_gpc_dim": (C.c_int, [_P]),
+    "gprc_gpr_dim": (C.c_int, [_P]),
     "gprc_gpc_free": (None, [_P]),
     "gprc_mvn_sample": (C.c_int, [_P, c_double_p, c_double_p, C.c_long, c_double_p, C.c_long, c_double_p, c_long_p]),
     "gprc_dist_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "gprc_dist_create": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(_P)]),
     "gprc_dist_free": (None, [_P]),
+    "gprc_dist_set_timeline": (C.c_int, [_P, C.c_int]),
+    "gprc_dist_get_timeline": (C.c_int, [_P, c_double_p, C.c_int, C.POINTER(C.c_int)]),
     "gprc_dist_gpr_fit": (C.c_int, [_P, _K, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double, c_double_p,
                                     c_double_p, c_long_p, c_double_p]),
     "gprc_dist_gpr_fit_replicated": (C.c_int, [_P, _K, c_double_p, C.c_int, C.c_long, c_double_p, C.c_double,

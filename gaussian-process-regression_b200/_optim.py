@@ -1,7 +1,10 @@
 """Host-side optimisers that drive fit(): restatements of R's ``optimize``/``optim(method = "Brent")`` engine
 (src/appl/fmin.c, Brent_fmin) and of ``optim(method = "BFGS")`` (src/appl/optim.c, vmmin), which R/fit.R:143-160
 calls.  They stay on the host: every objective / gradient evaluation they request is
-one call into libgprc."""
+one call into libgprc.
+
+Provenance / licence: see the header of csrc/optim.hpp (Brent 1973 / Nash 1990 algorithms; R's GPL-2+ C sources were read
+to reproduce constants, acceptance rules and counters exactly; independent restatement, no code copied)."""
 from __future__ import annotations
 
 import math

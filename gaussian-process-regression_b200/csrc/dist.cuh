@@ -174,4 +174,11 @@ struct gprc_dist {
   int rank = 0, world = 1;
   cudaStream_t s_comm = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_bcast[2] = {nullptr, nullptr}, ev_rest = nullptr, ev_begin = nullptr;
+  // optional per-panel timeline of the factorisation (gprc_dist_set_timeline): 6 timing events per panel --
+  // [0,1] look-ahead update + factorisation of panel p on its owner (high-priority stream), [2,3] broadcast of panel p
+  // (communication stream), [4,5] trailing update with panel p (main stream) -- read back relative to the start event
+  bool timeline_on = false;
+  int timeline_npan = 0;
+  std::vector<cudaEvent_t> timeline;  // npan * 6 (+ 1 origin)
+  std::vector<double> timeline_ms;    // resolved after the fit: npan * 6, NaN where this rank recorded nothing
 };

@@ -1,6 +1,7 @@
 // gprc.cu -- C ABI of libgprc (include/gprc.h): handles, host<->device plumbing and the launch sequences of the
 // GP hot path.  No Torch, no cuBLAS/cuSOLVER, no CPU fallback: every numerical step is one of the kernels in
 // cov.cuh / gemm.cuh / potrf.cuh / trsv.cuh / gpc.cuh.
+#include <chrono>
 #include <climits>
 #include <algorithm>
 
@@ -988,12 +989,19 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     // amortise the per-block-row launches and leave one short tail instead of one per 148-tile chunk.
     GPRC_CHECK(oz_factor_digits_any(c, F));  // before sizing the workspace: the digit planes of L take n_pad^2 S bytes
     GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 75.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad));
+    const bool trace_chunks = getenv("GPRC_TRACE_CHUNKS") != nullptr;  // diagnostics: host wall time per chunk on stderr
     for (long c0 = 0; c0 < m; c0 += ws.mc) {
       const long mcur = std::min(ws.mc, m - c0);
       if (c0 > 0) GPRC_CHECK(poll_interrupt(c));
+      const auto w0 = std::chrono::steady_clock::now();
       GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 4, dmean, dvar));
+      const auto w1 = std::chrono::steady_clock::now();
       GPRC_CUDA(cudaMemcpyAsync(c->h_info, ws.sched + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       GPRC_CUDA(cudaStreamSynchronize(c->stream));
+      if (trace_chunks)
+        fprintf(stderr, "[gprc] INT8 chunk at %ld (%ld points): enqueue %.1f ms, complete %.1f ms\n", c0, mcur,
+                std::chrono::duration<double, std::milli>(w1 - w0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
       const int flag = *reinterpret_cast<int*>(c->h_info);
       if (flag & ~3) return set_error(-6, __FILE__, __LINE__, "INT8 substitution kernel: a pipeline barrier never completed");
       if (flag) GPRC_CHECK(predict_chunk(c, k, dX, d, F, ws, weights, rowscale, dXs, c0, mcur, 2, dmean, dvar));
@@ -1443,6 +1451,7 @@ extern "C" int gprc_gpr_get(gprc_gpr* g, int what, double* host) {
   }
 }
 extern "C" long gprc_gpr_n(const gprc_gpr* g) { return g ? g->F.n : 0; }
+extern "C" int gprc_gpr_dim(const gprc_gpr* g) { return g ? g->d : 0; }
 extern "C" void gprc_gpr_free(gprc_gpr* g) {
   if (!g) return;
   DeviceGuard guard(g->ctx);
@@ -1949,7 +1958,9 @@ static int gpc_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, in
         break;
       }
       objective = c->h_scalars[0];
-      if (trace && it <= trace_cap) trace[it - 1] = objective;
+      // the LAST slot always holds the most recent objective (logq = objective - sum(diag(L)) needs the final one even
+      // when the loop runs for more than trace_cap iterations)
+      if (trace && trace_cap > 0) trace[std::min(it, trace_cap) - 1] = objective;
       // stopping rule, literally R/GPCclass.R:87-96 (the guard is mis-signed in the reference: SURVEY.md A.2)
       if (it > 1) {
         if (fabs(objective - last_objective) < eps) {
@@ -1963,6 +1974,7 @@ static int gpc_fit_common(gprc_ctx* c, const gprc_kernel* k, const double* X, in
       }
       last_objective = objective;
       if (max_iter > 0 && it >= max_iter) break;
+      if ((rc = poll_interrupt(c))) break;  // a loop that oscillates without converging must stay interruptible
       if (!(objective == objective)) {  // NaN objective can never satisfy the rule: the reference would spin forever
         *status = 2;
         break;
@@ -2149,6 +2161,7 @@ extern "C" int gprc_gpc_get(gprc_gpc* g, int what, double* host) {
   }
 }
 extern "C" long gprc_gpc_n(const gprc_gpc* g) { return g ? g->F.n : 0; }
+extern "C" int gprc_gpc_dim(const gprc_gpc* g) { return g ? g->d : 0; }
 extern "C" void gprc_gpc_free(gprc_gpc* g) {
   if (!g) return;
   DeviceGuard guard(g->ctx);
@@ -2365,6 +2378,7 @@ extern "C" void gprc_dist_free(gprc_dist* D) {
   cudaEventDestroy(D->ev_bcast[1]);
   cudaEventDestroy(D->ev_rest);
   cudaEventDestroy(D->ev_begin);
+  for (cudaEvent_t e : D->timeline) cudaEventDestroy(e);
   cudaStreamDestroy(D->s_comm);
   delete D;
 }
@@ -2423,6 +2437,22 @@ static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, in
     cudaEventCreate(&e1);
     cudaEventCreate(&e2);
     cudaEventCreate(&e3);
+    if (D->timeline_on) {
+      const size_t want = (size_t)npan * 6 + 1;
+      while (D->timeline.size() < want) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        D->timeline.push_back(ev);
+      }
+      D->timeline_npan = npan;
+      D->timeline_ms.assign((size_t)npan * 6, NAN);
+    }
+    std::vector<char> tl_set(D->timeline_on ? (size_t)npan * 6 : 0, 0);
+    auto tl = [&](int p, int slot, cudaStream_t st) {
+      if (!D->timeline_on) return;
+      cudaEventRecord(D->timeline[(size_t)p * 6 + slot + 1], st);
+      tl_set[(size_t)p * 6 + slot] = 1;
+    };
     cudaMemcpyAsync(dX, X, sizeof(double) * d * n, cudaMemcpyHostToDevice, s0);
     cudaMemsetAsync(dy, 0, sizeof(double) * n_pad, s0);
     cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, s0);
@@ -2523,14 +2553,19 @@ static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, in
     };
 
     GPRC_CUDA(cudaEventRecord(D->ev_begin, s0));
+    if (D->timeline_on) cudaEventRecord(D->timeline[0], s0);
     GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_begin, 0));
     GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_begin, 0));
     if (owner(0) == me) {
+      tl(0, 0, s1);
       if ((rc = factor_panel(0))) break;
+      tl(0, 1, s1);
       GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
     }
+    tl(0, 2, sc);
     GPRC_NCCL(api, api.Broadcast(Pbuf[0], Pbuf[0], (size_t)n_pad * PANEL + OUTER_BLOCKS * NB * NB, ncclDouble, owner(0),
                                  D->comm, sc));
+    tl(0, 3, sc);
     GPRC_CUDA(cudaEventRecord(D->ev_bcast[0], sc));
     for (int p = 0; p < npan && rc == 0; ++p) {
       const bool own_next = (p + 1 < npan) && owner(p + 1) == me;
@@ -2538,25 +2573,31 @@ static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, in
         // LA: bring panel p + 1 up to date with panel p, then factor it -- all on the high-priority stream
         GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_bcast[p & 1], 0));
         if (p > 0) GPRC_CUDA(cudaStreamWaitEvent(s1, D->ev_rest, 0));
+        tl(p + 1, 0, s1);
         if ((rc = update(p, p + 1, 1, s1))) break;
         if ((rc = factor_panel(p + 1))) break;
+        tl(p + 1, 1, s1);
       }
       if (p + 1 < npan) {
         // broadcast of panel p + 1 into the other buffer: it is free once update p - 1 has finished reading it
         if (p > 0) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_rest, 0));
         if (own_next) GPRC_CUDA(cudaStreamWaitEvent(sc, D->ev_packed, 0));
         const long rows = n_pad - (long)(p + 1) * PANEL;
+        tl(p + 1, 2, sc);
         GPRC_NCCL(api, api.Broadcast(Pbuf[(p + 1) & 1], Pbuf[(p + 1) & 1],
                                      (size_t)rows * PANEL + OUTER_BLOCKS * NB * NB, ncclDouble, owner(p + 1), D->comm,
                                      sc));
+        tl(p + 1, 3, sc);
         GPRC_CUDA(cudaEventRecord(D->ev_bcast[(p + 1) & 1], sc));
       }
       // rest(p): every owned panel right of p (and right of p + 1 if that one was just handled by LA)
       GPRC_CUDA(cudaStreamWaitEvent(s0, D->ev_bcast[p & 1], 0));
+      tl(p, 4, s0);
       if ((rc = unpack(p))) break;
       const int first = next_owned_after(own_next ? p + 1 : p);
       const int count = (first < npan) ? (npan - 1 - first) / N + 1 : 0;
       if ((rc = update(p, first, count, s0))) break;
+      tl(p, 5, s0);
       GPRC_CUDA(cudaEventRecord(D->ev_rest, s0));
     }
     if (rc) break;
@@ -2621,6 +2662,15 @@ static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, in
     }
     *info = (*c->h_info == LONG_MAX) ? 0 : *c->h_info;
     *logp = -0.5 * c->h_scalars[0] - c->h_scalars[1] - (double)n / 2.0 * log(2.0 * M_PI);
+    if (D->timeline_on) {
+      cudaStreamSynchronize(s1);
+      cudaStreamSynchronize(sc);
+      for (size_t q = 0; q < tl_set.size(); ++q) {
+        if (!tl_set[q]) continue;
+        float f = 0.f;
+        if (cudaEventElapsedTime(&f, D->timeline[0], D->timeline[q + 1]) == cudaSuccess) D->timeline_ms[q] = f;
+      }
+    }
     if (phase_ms) {
       float f = 0.f;
       cudaEventElapsedTime(&f, e0, e1);
@@ -2661,6 +2711,23 @@ static int dist_fit_impl(gprc_dist* D, const gprc_kernel* k, const double* X, in
   dfree(dy);
   dfree(partial);
   return rc;
+}
+
+extern "C" int gprc_dist_set_timeline(gprc_dist* D, int on) {
+  GPRC_ARG(D != nullptr);
+  D->timeline_on = on != 0;
+  return 0;
+}
+// ms: npan x 6 doubles (row p: look-ahead + factorisation begin / end on the owner, broadcast begin / end, trailing update
+// begin / end; milliseconds since the start of the factorisation on this rank's device; NaN = not recorded on this rank)
+extern "C" int gprc_dist_get_timeline(gprc_dist* D, double* ms, int cap_panels, int* npan) {
+  GPRC_ARG(D && npan);
+  *npan = D->timeline_npan;
+  if (ms) {
+    const int np = std::min(cap_panels, D->timeline_npan);
+    for (size_t q = 0; q < (size_t)np * 6 && q < D->timeline_ms.size(); ++q) ms[q] = D->timeline_ms[q];
+  }
+  return 0;
 }
 
 extern "C" int gprc_dist_gpr_fit(gprc_dist* D, const gprc_kernel* k, const double* X, int d, long n, const double* y,

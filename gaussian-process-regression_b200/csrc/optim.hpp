@@ -6,6 +6,15 @@
 // control flow; what it drives -- one Cholesky-based objective or gradient per evaluation -- runs on the device without
 // the data ever leaving it (gprc_fit_family).  The arithmetic follows the same statement order as the Python mirror
 // (_optim.py), which the CPU tier pins to R's documented example(optim) result, so both produce identical iterates.
+//
+// Provenance / licence: the ALGORITHMS are Brent's localmin (R. P. Brent, "Algorithms for Minimization without
+// Derivatives", 1973, ch. 5 -- the Fortran `fmin` on netlib is public domain) and the variable-metric method of J. C. Nash,
+// "Compact Numerical Methods for Computers", 2nd ed. 1990, Algorithm 21 (on which R's vmmin is based).  R's own C
+// sources (src/appl/fmin.c, src/appl/optim.c) are GPL-2 | GPL-3; they were READ to reproduce R's constants, tolerances,
+// step acceptance rule and counters exactly (so that trajectories match R's optim digit for digit) and are cited above
+// for that reason -- this file is an independent restatement written for this library, not a copy of those files.
+// A downstream that needs licence certainty for trajectory-identical behaviour should treat optim.hpp and _optim.py as
+// derived from GPL-2+ material; nothing else in libgprc depends on them (fit() can be driven by any optimiser).
 #pragma once
 #include <cmath>
 #include <functional>

@@ -9,6 +9,12 @@
 // would flip class labels against the reference.
 // The file compiles as plain C++ (tests build a host library from it and compare with scipy.integrate.quad, which
 // wraps the same QUADPACK routine) and as CUDA (one thread per test point).
+//
+// Provenance / licence: QUADPACK (R. Piessens, E. de Doncker-Kapenga, C. W. Ueberhuber, D. K. Kahaner, "QUADPACK: A
+// Subroutine Package for Automatic Integration", Springer 1983; Fortran sources on netlib) is in the PUBLIC DOMAIN.  This
+// file is a new C++/CUDA restatement of the published algorithms dqagie / dqk15i / dqpsrt / dqelg; no code was taken from
+// R's integrate.c (GPL-2) or from /root/reference (which holds no native code).  It is part of libgprc and carries the
+// repository's licence.
 #pragma once
 #include <cfloat>
 #include <cmath>

@@ -101,6 +101,9 @@ SEXP C_gprc_gpr_predict(SEXP ptr, SEXP Xs, SEXP Ks, SEXP kss) {
   gprc_gpr* g = (gprc_gpr*)R_ExternalPtrAddr(ptr);
   if (!g) Rf_error("gprc: model handle is NULL (restored from saveRDS?); rebuild with GPR$new");
   const long m = (Ks == R_NilValue) ? Rf_ncols(Xs) : Rf_ncols(Ks);
+  /* the library reads d x m (or n x m) doubles: a matrix with the wrong number of rows must never reach it */
+  if (Ks == R_NilValue ? Rf_nrows(Xs) != gprc_gpr_dim(g) : Rf_nrows(Ks) != gprc_gpr_n(g) || Rf_length(kss) != m)
+    Rf_error("non-conformable arrays");
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 2));
   int rc = (Ks == R_NilValue) ? gprc_gpr_predict(g, REAL(Xs), m, REAL(out), REAL(out) + m)
                               : gprc_gpr_predict_precomputed(g, REAL(Ks), REAL(kss), m, REAL(out), REAL(out) + m);
@@ -114,6 +117,7 @@ SEXP C_gprc_gpr_predict_cov(SEXP ptr, SEXP Xs) {
   gprc_gpr* g = (gprc_gpr*)R_ExternalPtrAddr(ptr);
   if (!g) Rf_error("gprc: model handle is NULL");
   const long m = Rf_ncols(Xs);
+  if (Rf_nrows(Xs) != gprc_gpr_dim(g)) Rf_error("non-conformable arrays");
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
   SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 1));
   SEXP cov = PROTECT(Rf_allocMatrix(REALSXP, (int)m, (int)m));
@@ -192,6 +196,9 @@ SEXP C_gprc_gpc_predict_latent(SEXP ptr, SEXP Xs, SEXP Ks, SEXP kss) {
   gprc_gpc* g = (gprc_gpc*)R_ExternalPtrAddr(ptr);
   if (!g) Rf_error("gprc: model handle is NULL");
   const long m = (Ks == R_NilValue) ? Rf_ncols(Xs) : Rf_ncols(Ks);
+  /* the library reads d x m (or n x m) doubles: a matrix with the wrong number of rows must never reach it */
+  if (Ks == R_NilValue ? Rf_nrows(Xs) != gprc_gpc_dim(g) : Rf_nrows(Ks) != gprc_gpc_n(g) || Rf_length(kss) != m)
+    Rf_error("non-conformable arrays");
   SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 2));
   int rc = (Ks == R_NilValue) ? gprc_gpc_predict_latent(g, REAL(Xs), m, REAL(out), REAL(out) + m)
                               : gprc_gpc_predict_latent_precomputed(g, REAL(Ks), REAL(kss), m, REAL(out), REAL(out) + m);
@@ -210,6 +217,7 @@ SEXP C_gprc_gpc_predict_class(SEXP ptr, SEXP Xs) {
   gprc_gpc* g = (gprc_gpc*)R_ExternalPtrAddr(ptr);
   if (!g) Rf_error("gprc: model handle is NULL");
   const long m = Rf_ncols(Xs);
+  if (Rf_nrows(Xs) != gprc_gpc_dim(g)) Rf_error("non-conformable arrays");
   SEXP out = PROTECT(Rf_allocVector(REALSXP, m));
   int* ier = (int*)R_alloc((size_t)m, sizeof(int));
   int rc = gprc_gpc_predict_class(g, REAL(Xs), m, REAL(out), ier);

@@ -168,6 +168,9 @@ int gprc_gpr_predict_grid(gprc_gpr* g, const double* limits, int per_dim, double
 int gprc_gpr_predict_cov(gprc_gpr* g, const double* Xs, long m, double* mean, double* cov);
 int gprc_gpr_get(gprc_gpr* g, int what, double* host);
 long gprc_gpr_n(const gprc_gpr* g);
+/* nrow(X) of the model (0 for a closure-kernel model): the shim checks nrow(X_star) against it before any buffer of
+   d x m doubles is read (the reference fails with "non-conformable arrays" in covariance_matrix, R/GPRclass.R:356) */
+int gprc_gpr_dim(const gprc_gpr* g);
 void gprc_gpr_free(gprc_gpr* g);
 
 /* ---- fit(): log marginal likelihood and gradient -- dens / dens_deriv, R/fit.R:117-139 -------------------- */
@@ -235,6 +238,7 @@ int gprc_gpc_predict_class(gprc_gpc* g, const double* Xs, long m, double* prob, 
 int gprc_logistic_gaussian(gprc_ctx* ctx, const double* mean, const double* sd, long m, double* out, int* ier);
 int gprc_gpc_get(gprc_gpc* g, int what, double* host);
 long gprc_gpc_n(const gprc_gpc* g);
+int gprc_gpc_dim(const gprc_gpc* g); /* as gprc_gpr_dim */
 void gprc_gpc_free(gprc_gpc* g);
 
 /* ---- posterior sampling helper ------------------------------------------------------------- */
@@ -253,6 +257,12 @@ typedef struct gprc_dist gprc_dist;
 int gprc_dist_unique_id(char* id128, const char* nccl_path /* nullable: libnccl.so.2 */);
 int gprc_dist_create(gprc_ctx* ctx, const char* id128, int rank, int world, const char* nccl_path, gprc_dist** out);
 void gprc_dist_free(gprc_dist* d);
+/* Per-panel timeline of the distributed factorisation (evidence for the layout choice): when switched
+   on, the next gprc_dist_gpr_fit* records CUDA events around, per 512-column panel p, [0,1] the look-ahead update +
+   factorisation on its owner, [2,3] its ncclBroadcast, [4,5] the trailing update with it; gprc_dist_get_timeline returns
+   npan x 6 milliseconds since the start of the factorisation on this rank (NaN where this rank recorded nothing). */
+int gprc_dist_set_timeline(gprc_dist* D, int on);
+int gprc_dist_get_timeline(gprc_dist* D, double* ms, int cap_panels, int* npan);
 /* Collective.  X (d x n), y: HOST, identical on every rank.  alpha (n, host, nullable) and logp are returned on every
  * rank.  phase_ms (nullable, 4): build, factor, solve, total -- CUDA events on this rank's stream. */
 int gprc_dist_gpr_fit(gprc_dist* d, const gprc_kernel* k, const double* X, int dim, long n, const double* y,

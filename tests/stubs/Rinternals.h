@@ -24,6 +24,7 @@ int Rf_asInteger(SEXP);
 int Rf_asLogical(SEXP);
 double Rf_asReal(SEXP);
 int Rf_nrows(SEXP);
+int Rf_length(SEXP);
 int Rf_ncols(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);

@@ -94,6 +94,19 @@ def test_predict_vector_reshape_rule(gprc, oracle):
         g.predict(np.zeros(3))
 
 
+def test_predict_rejects_a_matrix_with_the_wrong_number_of_rows(gprc):
+    """a (1, m) matrix with D = 2 passes length(X_star) %% nrow(X) == 0 (R/GPRclass.R:156) and must fail like the
+    reference's covariance_matrix does, never reach the library (which would read D * m doubles from it)"""
+    rng = np.random.default_rng(3)
+    g = gprc.GPR(rng.uniform(-1, 1, (2, 30)), rng.normal(size=30), 0.1, gprc.cov_func(gprc.sqrexp, l=1.0))
+    for bad in (np.zeros((1, 8)), np.zeros((3, 4))):
+        with pytest.raises(ValueError, match="non-conformable"):
+            g.predict(bad)
+        with pytest.raises(ValueError, match="non-conformable"):
+            g.predict(bad, pointwise_var=False)
+    assert g.predict(np.zeros(8)).shape == (4, 2)          # a bare vector is reshaped to D rows (R/GPRclass.R:157-159)
+
+
 def test_predict_full_covariance(gprc, oracle):
     rng = np.random.default_rng(4)
     X = rng.uniform(-5, 5, (1, 150))

@@ -205,3 +205,39 @@ def test_numpy_emulation_uses_the_kernels_digits(S):
     assert not rows[:, 0].any()                                  # no overflow flags
     want = np.stack([d for d in sim.digits(x, np.full(len(x), e), S)], axis=1).astype(int)
     np.testing.assert_array_equal(rows[:, 1:], want)
+
+
+def test_blocked_cholesky_and_solves_equal_lapack():
+    """oracle.blocked_cholesky_inplace / blocked_solve_lower carry n^2 > 2^31 (SciPy's LP64 LAPACK segfaults there):
+    against dpotrf / dtrtrs at a size both can run, with a block size that leaves a ragged last block."""
+    import scipy.linalg
+    rng = np.random.default_rng(11)
+    n = 1111
+    B = rng.standard_normal((n, 90))
+    A = np.asfortranarray(B @ B.T + 0.3 * np.eye(n))
+    ref = scipy.linalg.cholesky(A, lower=True)
+    L = o.blocked_cholesky_inplace(A.copy(order="F"), nb=256)
+    assert np.max(np.abs(np.tril(L) - ref)) < 1e-12 * np.max(np.abs(ref))
+    rhs = rng.standard_normal((n, 7))
+    np.testing.assert_allclose(o.blocked_solve_lower(L, rhs, nb=256), scipy.linalg.solve_triangular(ref, rhs, lower=True),
+                               rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(o.blocked_solve_lower(L, rhs[:, 0], trans=True, nb=256),
+                               scipy.linalg.solve_triangular(ref, rhs[:, 0], lower=True, trans="T"), rtol=1e-10, atol=1e-12)
+
+
+def test_full_size_golden_sample_is_consistent():
+    """tests/golden/c4_full_sample.npz (oracle at n = 50 000, tests/golden/make_c4_golden.py): generator bits, shapes and
+    the size-independent properties 0 < var <= k** = 1, logp = -y'alpha/2 - sum log diag L - n/2 log 2 pi."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "c4_full_sample.npz")
+    z = np.load(path)
+    n, m, d, M = int(z["n"]), int(z["m"]), int(z["d"]), int(z["M"])
+    assert (n, m, d) == (50000, 1000000, 8) and z["mean"].shape == (M,) and z["var"].shape == (M,)
+    rng = np.random.default_rng(int(z["seed"]))
+    X = rng.uniform(-1, 1, size=(d, n))
+    rng.normal(0, 0.1, n)
+    Xs = rng.uniform(-1, 1, size=(d, m))
+    np.testing.assert_array_equal(Xs[:, :M], z["Xs_head"])
+    assert np.all(z["var"] > 0) and np.all(z["var"] <= 1.0)
+    assert abs(float(z["logp"]) - (-0.5 * float(z["yalpha"]) - float(z["sumlogdiag"]) - n / 2 * math.log(2 * math.pi))) < 1e-6
+    # L[i, j] samples: |L_ij| <= sqrt(K_ii) = sqrt(1.01); the diagonal head is positive
+    assert np.all(np.abs(z["L_vals"]) <= math.sqrt(1.01) + 1e-12) and np.all(z["diagL_head"] > 0)
