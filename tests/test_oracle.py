@@ -219,10 +219,10 @@ def test_blocked_cholesky_and_solves_equal_lapack():
     L = o.blocked_cholesky_inplace(A.copy(order="F"), nb=256)
     assert np.max(np.abs(np.tril(L) - ref)) < 1e-12 * np.max(np.abs(ref))
     rhs = rng.standard_normal((n, 7))
-    np.testing.assert_allclose(o.blocked_solve_lower(L, rhs, nb=256), scipy.linalg.solve_triangular(ref, rhs, lower=True),
-                               rtol=1e-10, atol=1e-12)
-    np.testing.assert_allclose(o.blocked_solve_lower(L, rhs[:, 0], trans=True, nb=256),
-                               scipy.linalg.solve_triangular(ref, rhs[:, 0], lower=True, trans="T"), rtol=1e-10, atol=1e-12)
+    want = scipy.linalg.solve_triangular(ref, rhs, lower=True)
+    assert np.max(np.abs(o.blocked_solve_lower(L, rhs, nb=256) - want)) < 1e-11 * np.max(np.abs(want))
+    want = scipy.linalg.solve_triangular(ref, rhs[:, 0], lower=True, trans="T")
+    assert np.max(np.abs(o.blocked_solve_lower(L, rhs[:, 0], trans=True, nb=256) - want)) < 1e-11 * np.max(np.abs(want))
 
 
 def test_full_size_golden_sample_is_consistent():
