@@ -637,11 +637,15 @@ static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long 
                             double extra_bytes_per_col = 0.0) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
+  // blocks parked in this context's caching pool are available too (pool_alloc gives them back to the driver and retries
+  // when cudaMalloc fails); without them the chunk size shrank from step to step as differently sized workspaces piled
+  // up in the pool (27 chunks instead of 11 for 10^6 test points at n = 50 000)
+  free_b += c->pool_cached_bytes;
   long want = round_up(std::max<long>(m, 1), NB);
   // per test point: Ks column + partial rows
   // (+ the INT8 path's digit planes of V, allocated by its variance pass)
   const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1) + extra_bytes_per_col;
-  const double budget = std::min(max_bytes, 0.45 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
+  const double budget = std::min(max_bytes, 0.5 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
   long cap = (long)(budget / per_col) / NB * NB;
   cap = std::max<long>(cap, NB);
   cap = std::min<long>(cap, 1L << 20);
