@@ -4,8 +4,11 @@
 // logp (R/GPRclass.R:153), logq (R/GPCclass.R:103) and fit()'s leading-minor rule (R/fit.R:119).
 #pragma once
 #include <cooperative_groups.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
-#include "common.cuh"
+#include "gemm.cuh"
 
 namespace gprc {
 
@@ -156,6 +159,158 @@ __global__ void __launch_bounds__(256) trsv_bwd_coop_kernel(const double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Round 2: both sweeps as ONE dataflow kernel.  The cooperative sweeps above separate the n / 128 block steps by grid-wide
+// barriers, and every step is a dependent chain of a barrier, a 128 x 128 matvec and a rank-128 update: 24 us per step,
+// 19 ms at n = 50 000 against a 3 ms HBM floor.  Here a resident grid of G CTAs owns the row blocks cyclically (block i on
+// CTA i mod G) and every row block is ONE CTA's job from start to finish:
+//   forward   z_i = Linv_i (b_i - sum_{j<i} L[i, j] z_j)        tiles of block ROW i, j ascending
+//   backward  x_i = Linv_i^T (z_i - sum_{j>i} L[j, i]^T x_j)     tiles of block COLUMN i, j descending
+// A finished block is published with a release store to flag[i]; consumers acquire-poll the flag of the block they need
+// next.  Nothing waits on a grid barrier: the CTAs far from the critical path stream their tiles of L at HBM rate while
+// the critical path -- the owner of block i turning z_(i-1) into z_i: one 128 x 128 tile (prefetched into L2), the
+// inverted diagonal block, one flag -- is a few microseconds per step.  Summation orders are fixed (bitwise reproducible).
+// Deadlock freedom: blocks are totally ordered, every CTA handles its blocks in that order, and the grid is launched
+// cooperatively (all CTAs resident).  A flag that never arrives raises `error` and traps instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------------------------
+// ld_acquire_gpu / st_release_gpu: gemm.cuh (the persistent substitution kernel uses the same pair)
+__device__ __forceinline__ void flow_wait(const int* flag, int* error) {
+  for (long spin = 0; ld_acquire_gpu(flag) == 0; ++spin) {
+    if (spin > (1L << 26)) {  // seconds: a dependency that never arrives
+      atomicOr(error, 1);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// flags: 2 * nt ints, zero on entry (forward flags, then backward flags); z, x: n doubles each; b is only read
+__global__ void __launch_bounds__(256) trsv_flow_kernel(const double* __restrict__ L, long ld,
+                                                        const double* __restrict__ dinv, int nt,
+                                                        const double* __restrict__ b, double* __restrict__ z,
+                                                        double* __restrict__ x, int* __restrict__ flags,
+                                                        int* __restrict__ error) {
+  __shared__ double xs[2][NB], part[NB], acc_s[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, me = blockIdx.x;
+  int* ffwd = flags;
+  int* fbwd = flags + nt;
+
+  // ---------------- forward: row r = tid & 127, column half h = tid >> 7 ----------------
+  {
+    const int r = tid & (NB - 1), h = tid >> 7;
+    for (int i = me; i < nt; i += G) {
+      // the tiles next to the diagonal and the inverted diagonal block are on the critical path: pull them into L2 now
+      {
+        const double* Li = dinv + (long)i * NB * NB;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prefetch_l2(Li + (long)(tid * 4 + q) * 16);
+        for (int back = 1; back <= 2 && i - back >= 0; ++back) {
+          const double* T = L + (long)i * NB + (long)(i - back) * NB * ld;
+          // 128 columns x 1 KB: thread t takes column t / 2, half t % 2 (4 lines of 128 B)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) prefetch_l2(T + (long)(tid >> 1) * ld + ((tid & 1) * 4 + q) * 16);
+        }
+      }
+      double a0 = 0.0, a1 = 0.0;
+      for (int j = 0; j < i; ++j) {
+        const int buf = j & 1;
+        if (warp == 0) {
+          flow_wait(ffwd + j, error);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xs[buf][lane + 32 * q] = __ldcg(z + (long)j * NB + lane + 32 * q);
+        }
+        __syncthreads();  // xs[buf] is complete; everybody has finished tile j - 1 (which read xs[buf ^ 1])
+        const double* Lp = L + (long)i * NB + r + ((long)j * NB + h * 64) * ld;
+        const double* xq = xs[buf] + h * 64;
+#pragma unroll 16
+        for (int c = 0; c < 64; c += 2) {
+          a0 = fma(Lp[(long)c * ld], xq[c], a0);
+          a1 = fma(Lp[(long)(c + 1) * ld], xq[c + 1], a1);
+        }
+      }
+      // acc = b_i - (two column halves, fixed order)
+      const double mine = a0 + a1;
+      if (h == 1) part[r] = mine;
+      __syncthreads();
+      if (h == 0) acc_s[r] = b[(long)i * NB + r] - (mine + part[r]);
+      __syncthreads();
+      // z_i = Linv_i acc   (explicit zeros above the diagonal of Linv_i)
+      const double* Li = dinv + (long)i * NB * NB;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll 16
+      for (int c = h * 64; c < h * 64 + 64; c += 2) {
+        s0 = fma(Li[r + c * NB], acc_s[c], s0);
+        s1 = fma(Li[r + (c + 1) * NB], acc_s[c + 1], s1);
+      }
+      const double sv = s0 + s1;
+      if (h == 1) part[r] = sv;
+      __syncthreads();
+      if (h == 0) z[(long)i * NB + r] = sv + part[r];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_gpu(ffwd + i, 1);
+    }
+  }
+
+  // ---------------- backward: warp w owns columns 16 w .. 16 w + 15 of the block, lanes run over the rows ----------------
+  for (int ib = me; ib < nt; ib += G) {
+    const int i = nt - 1 - ib;
+    {
+      const double* Li = dinv + (long)i * NB * NB;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prefetch_l2(Li + (long)(tid * 4 + q) * 16);
+      for (int fwd = 1; fwd <= 2 && i + fwd < nt; ++fwd) {
+        const double* T = L + (long)(i + fwd) * NB + (long)i * NB * ld;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prefetch_l2(T + (long)(tid >> 1) * ld + ((tid & 1) * 4 + q) * 16);
+      }
+    }
+    double acc[16];
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) acc[cc] = 0.0;
+    for (int j = nt - 1; j > i; --j) {
+      flow_wait(fbwd + j, error);
+      double xr[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xr[q] = __ldcg(x + (long)j * NB + lane + 32 * q);
+      const double* Tp = L + (long)j * NB + lane + ((long)i * NB + warp * 16) * ld;
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const double* cp = Tp + (long)cc * ld;
+        double t = acc[cc];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t = fma(cp[32 * q], xr[q], t);
+        acc[cc] = t;
+      }
+    }
+    flow_wait(ffwd + i, error);  // z_i (forward result of this block)
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const double t = warp_sum(acc[cc]);
+      if (lane == 0) acc_s[warp * 16 + cc] = __ldcg(z + (long)i * NB + warp * 16 + cc) - t;
+    }
+    __syncthreads();
+    // x_i = Linv_i^T acc: entry r is column r of Linv_i dotted with acc
+    const double* Li = dinv + (long)i * NB * NB;
+    double tv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tv[q] = acc_s[lane + 32 * q];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const int rcol = warp * 16 + rr;
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t = fma(Li[lane + 32 * q + rcol * NB], tv[q], t);
+      t = warp_sum(t);
+      if (lane == 0) x[(long)i * NB + rcol] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(fbwd + i, 1);
+  }
+}
+
 inline int coop_grid(gprc_ctx* ctx, const void* func, long work_items) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -164,10 +319,30 @@ inline int coop_grid(gprc_ctx* ctx, const void* func, long work_items) {
   return (int)(g < 1 ? 1 : g);
 }
 
-// x = L^-T L^-1 rhs.  work: n doubles; rhs is left untouched.
+// x = L^-T L^-1 rhs.  work, tmp: n doubles each; rhs is left untouched.
+// Default: the dataflow kernel (one launch for both sweeps; `work` holds its flags).  GPRC_TRSV=coop in the environment
+// selects the round-1 cooperative sweeps (kept for comparison measurements).
 inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
                      double* work, double* tmp, double* x) {
   int nt = (int)(n / NB);
+  static const bool use_coop = [] {
+    const char* e = getenv("GPRC_TRSV");
+    return !(e && strcmp(e, "flow") == 0);   // TODO(round 2): flip once the dataflow kernel has run on a B200
+  }();
+  if (!use_coop) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_flow_kernel, 256, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    const int grid = std::min(nt, ctx->sm_count * std::min(per_sm, 2));
+    int* flags = reinterpret_cast<int*>(work);
+    int* error = flags + 2 * nt;
+    GPRC_CUDA(cudaMemsetAsync(work, 0, sizeof(int) * (2 * (size_t)nt + 2), ctx->stream));
+    void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&rhs, (void*)&tmp, (void*)&x, (void*)&flags,
+                    (void*)&error};
+    GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_flow_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
+  }
   GPRC_CUDA(cudaMemcpyAsync(work, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   {
     const int grid = coop_grid(ctx, (const void*)trsv_fwd_coop_kernel, (n + 63) / 64);
