@@ -366,6 +366,11 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
     c->opt_int8_tile = value;
     return 0;
   }
+  if (option == GPRC_OPT_TRSV) {
+    GPRC_ARG(value == 0 || value == 1);
+    c->opt_trsv = value;
+    return 0;
+  }
   if (option == GPRC_OPT_INT8_AUTO) {
     c->opt_int8_auto = value ? 1 : 0;
     return 0;

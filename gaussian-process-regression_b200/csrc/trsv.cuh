@@ -320,15 +320,12 @@ inline int coop_grid(gprc_ctx* ctx, const void* func, long work_items) {
 }
 
 // x = L^-T L^-1 rhs.  work, tmp: n doubles each; rhs is left untouched.
-// Default: the dataflow kernel (one launch for both sweeps; `work` holds its flags).  GPRC_TRSV=coop in the environment
-// selects the round-1 cooperative sweeps (kept for comparison measurements).
+// GPRC_OPT_TRSV = 1: the dataflow kernel (one launch for both sweeps; `work` holds its flags); 0: the round-1 cooperative
+// sweeps with grid-wide barriers.
 inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const double* dinv, const double* rhs,
                      double* work, double* tmp, double* x) {
   int nt = (int)(n / NB);
-  static const bool use_coop = [] {
-    const char* e = getenv("GPRC_TRSV");
-    return !(e && strcmp(e, "flow") == 0);   // TODO(round 2): flip once the dataflow kernel has run on a B200
-  }();
+  const bool use_coop = ctx->opt_trsv == 0;
   if (!use_coop) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_flow_kernel, 256, 0) != cudaSuccess || per_sm < 1)
