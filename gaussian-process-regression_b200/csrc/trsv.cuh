@@ -184,115 +184,174 @@ __device__ __forceinline__ void flow_wait(const int* flag, int* error) {
   }
 }
 
-// flags: 2 * nt ints, zero on entry (forward flags, then backward flags); z, x: n doubles each; b is only read
-__global__ void __launch_bounds__(256) trsv_flow_kernel(const double* __restrict__ L, long ld,
-                                                        const double* __restrict__ dinv, int nt,
-                                                        const double* __restrict__ b, double* __restrict__ z,
-                                                        double* __restrict__ x, int* __restrict__ flags,
-                                                        int* __restrict__ error) {
-  __shared__ double xs[2][NB], part[NB], acc_s[NB];
+// z and x (n doubles each) must be filled with the sentinel bit pattern 0xFF..FF (a NaN no arithmetic produces) before
+// the launch: a block is published simply by storing its 128 results, and a consumer polls the very elements it needs
+// until they differ from the sentinel -- one L2 round trip instead of flag + data, no fences.  Results that are NaN
+// themselves are stored as the canonical quiet NaN.
+constexpr unsigned long long TRSV_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+constexpr int TRSV_FLOW_SMEM = NB * NB * 8 + 2 * NB * 8;  // inverted diagonal block + two 128-vectors
+
+__device__ __forceinline__ double flow_poll(const double* p, int* error) {
+  unsigned long long v;
+  long spin = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (v != TRSV_SENTINEL) break;
+    if (++spin > (1L << 26)) {  // seconds: a dependency that never arrives
+      atomicOr(error, 1);
+      __threadfence_system();
+      __trap();
+    }
+  }
+  return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void flow_publish(double* p, double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  if (v != v) u = 0x7FF8000000000000ull;  // never the sentinel
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(u) : "memory");
+}
+
+// The units of work are half tiles (128 x 64 forward, 64 x 128 backward), double-buffered in registers: while one unit is
+// multiplied, the loads of the next are in flight (64 KB per CTA), and the loads of the unit next to the diagonal are
+// issued BEFORE its right-hand side is polled, so that the critical path per block step is: poll -> 32 FMAs ->
+// combine -> 128 x 128 matvec with the inverted diagonal block from shared memory -> store.
+__global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restrict__ L, long ld,
+                                                           const double* __restrict__ dinv, int nt,
+                                                           const double* __restrict__ b, double* __restrict__ z,
+                                                           double* __restrict__ x, int* __restrict__ error) {
+  extern __shared__ __align__(16) unsigned char flow_raw[];
+  double* Ls = reinterpret_cast<double*>(flow_raw);  // Linv_i, column-major 128 x 128
+  double* part = Ls + NB * NB;                       // [128]
+  double* acc_s = part + NB;                         // [128]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, me = blockIdx.x;
-  int* ffwd = flags;
-  int* fbwd = flags + nt;
 
-  // ---------------- forward: row r = tid & 127, column half h = tid >> 7 ----------------
+  // ---------------- forward: thread = (row r, 32-column half h of the current 64-column unit) ----------------
   {
     const int r = tid & (NB - 1), h = tid >> 7;
     for (int i = me; i < nt; i += G) {
-      // the tiles next to the diagonal and the inverted diagonal block are on the critical path: pull them into L2 now
+      __syncthreads();  // the previous block's readers of Ls / acc_s are done
       {
         const double* Li = dinv + (long)i * NB * NB;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) prefetch_l2(Li + (long)(tid * 4 + q) * 16);
-        for (int back = 1; back <= 2 && i - back >= 0; ++back) {
-          const double* T = L + (long)i * NB + (long)(i - back) * NB * ld;
-          // 128 columns x 1 KB: thread t takes column t / 2, half t % 2 (4 lines of 128 B)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) prefetch_l2(T + (long)(tid >> 1) * ld + ((tid & 1) * 4 + q) * 16);
-        }
+        for (int e = tid; e < NB * NB / 2; e += 256)
+          reinterpret_cast<double2*>(Ls)[e] = __ldg(reinterpret_cast<const double2*>(Li) + e);
       }
+      const double* Lrow = L + (long)i * NB + r + (long)(h * 32) * ld;  // unit u adds 64 u columns
+      const double* zq = z + h * 32 + lane;                              // unit u adds 64 u
+      double A[32], B[32];
       double a0 = 0.0, a1 = 0.0;
-      for (int j = 0; j < i; ++j) {
-        const int buf = j & 1;
-        if (warp == 0) {
-          flow_wait(ffwd + j, error);
+      const int units = 2 * i;
+      if (units > 0) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xs[buf][lane + 32 * q] = __ldcg(z + (long)j * NB + lane + 32 * q);
+        for (int c = 0; c < 32; ++c) A[c] = Lrow[(long)c * ld];
+      }
+      for (int u = 0; u < units; u += 2) {
+        {  // unit u + 1 -> B (always exists: two units per tile)
+          const double* p = Lrow + (long)(u + 1) * 64 * ld;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) B[c] = p[(long)c * ld];
         }
-        __syncthreads();  // xs[buf] is complete; everybody has finished tile j - 1 (which read xs[buf ^ 1])
-        const double* Lp = L + (long)i * NB + r + ((long)j * NB + h * 64) * ld;
-        const double* xq = xs[buf] + h * 64;
-#pragma unroll 16
-        for (int c = 0; c < 64; c += 2) {
-          a0 = fma(Lp[(long)c * ld], xq[c], a0);
-          a1 = fma(Lp[(long)(c + 1) * ld], xq[c + 1], a1);
+        {
+          const double zl = flow_poll(zq + (long)u * 64, error);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            a0 = fma(A[c], __shfl_sync(0xffffffffu, zl, c), a0);
+            a1 = fma(A[c + 1], __shfl_sync(0xffffffffu, zl, c + 1), a1);
+          }
+        }
+        if (u + 2 < units) {
+          const double* p = Lrow + (long)(u + 2) * 64 * ld;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) A[c] = p[(long)c * ld];
+        }
+        {
+          const double zl = flow_poll(zq + (long)(u + 1) * 64, error);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            a0 = fma(B[c], __shfl_sync(0xffffffffu, zl, c), a0);
+            a1 = fma(B[c + 1], __shfl_sync(0xffffffffu, zl, c + 1), a1);
+          }
         }
       }
-      // acc = b_i - (two column halves, fixed order)
+      // acc = b_i - (the two column halves, fixed order)
       const double mine = a0 + a1;
       if (h == 1) part[r] = mine;
-      __syncthreads();
+      __syncthreads();  // also: Ls is complete
       if (h == 0) acc_s[r] = b[(long)i * NB + r] - (mine + part[r]);
       __syncthreads();
       // z_i = Linv_i acc   (explicit zeros above the diagonal of Linv_i)
-      const double* Li = dinv + (long)i * NB * NB;
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll 16
       for (int c = h * 64; c < h * 64 + 64; c += 2) {
-        s0 = fma(Li[r + c * NB], acc_s[c], s0);
-        s1 = fma(Li[r + (c + 1) * NB], acc_s[c + 1], s1);
+        s0 = fma(Ls[r + c * NB], acc_s[c], s0);
+        s1 = fma(Ls[r + (c + 1) * NB], acc_s[c + 1], s1);
       }
       const double sv = s0 + s1;
       if (h == 1) part[r] = sv;
       __syncthreads();
-      if (h == 0) z[(long)i * NB + r] = sv + part[r];
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release_gpu(ffwd + i, 1);
+      if (h == 0) flow_publish(z + (long)i * NB + r, sv + part[r]);
     }
   }
 
-  // ---------------- backward: warp w owns columns 16 w .. 16 w + 15 of the block, lanes run over the rows ----------------
+  // ---------------- backward: warp w owns columns 16 w .. 16 w + 15 of the block, lane l rows l and l + 32 of the
+  // current 64-row unit ----------------
   for (int ib = me; ib < nt; ib += G) {
     const int i = nt - 1 - ib;
+    __syncthreads();
     {
       const double* Li = dinv + (long)i * NB * NB;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) prefetch_l2(Li + (long)(tid * 4 + q) * 16);
-      for (int fwd = 1; fwd <= 2 && i + fwd < nt; ++fwd) {
-        const double* T = L + (long)(i + fwd) * NB + (long)i * NB * ld;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) prefetch_l2(T + (long)(tid >> 1) * ld + ((tid & 1) * 4 + q) * 16);
-      }
+      for (int e = tid; e < NB * NB / 2; e += 256)
+        reinterpret_cast<double2*>(Ls)[e] = __ldg(reinterpret_cast<const double2*>(Li) + e);
     }
-    double acc[16];
+    const double* Lcol = L + lane + ((long)i * NB + warp * 16) * ld;  // unit: rows 64 v .. 64 v + 63, v descending
+    double A[32], B[32], acc[16];
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) acc[cc] = 0.0;
-    for (int j = nt - 1; j > i; --j) {
-      flow_wait(fbwd + j, error);
-      double xr[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) xr[q] = __ldcg(x + (long)j * NB + lane + 32 * q);
-      const double* Tp = L + (long)j * NB + lane + ((long)i * NB + warp * 16) * ld;
+    const int vhi = 2 * nt - 1, vlo = 2 * (i + 1);  // units vhi, vhi - 1, ..., vlo  (an even number of them)
+    if (vhi >= vlo) {
+      const double* p = Lcol + (long)vhi * 64;
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) {
-        const double* cp = Tp + (long)cc * ld;
-        double t = acc[cc];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t = fma(cp[32 * q], xr[q], t);
-        acc[cc] = t;
+        A[2 * cc] = p[(long)cc * ld];
+        A[2 * cc + 1] = p[(long)cc * ld + 32];
       }
     }
-    flow_wait(ffwd + i, error);  // z_i (forward result of this block)
+    for (int v = vhi; v >= vlo; v -= 2) {
+      {
+        const double* p = Lcol + (long)(v - 1) * 64;
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          B[2 * cc] = p[(long)cc * ld];
+          B[2 * cc + 1] = p[(long)cc * ld + 32];
+        }
+      }
+      {
+        const double x0 = flow_poll(x + (long)v * 64 + lane, error), x1 = flow_poll(x + (long)v * 64 + lane + 32, error);
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) acc[cc] = fma(A[2 * cc + 1], x1, fma(A[2 * cc], x0, acc[cc]));
+      }
+      if (v - 2 >= vlo) {
+        const double* p = Lcol + (long)(v - 2) * 64;
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          A[2 * cc] = p[(long)cc * ld];
+          A[2 * cc + 1] = p[(long)cc * ld + 32];
+        }
+      }
+      {
+        const double x0 = flow_poll(x + (long)(v - 1) * 64 + lane, error),
+                     x1 = flow_poll(x + (long)(v - 1) * 64 + lane + 32, error);
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) acc[cc] = fma(B[2 * cc + 1], x1, fma(B[2 * cc], x0, acc[cc]));
+      }
+    }
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
       const double t = warp_sum(acc[cc]);
-      if (lane == 0) acc_s[warp * 16 + cc] = __ldcg(z + (long)i * NB + warp * 16 + cc) - t;
+      if (lane == cc) acc_s[warp * 16 + cc] = flow_poll(z + (long)i * NB + warp * 16 + cc, error) - t;  // z_i: forward result
     }
-    __syncthreads();
+    __syncthreads();  // acc_s and Ls complete
     // x_i = Linv_i^T acc: entry r is column r of Linv_i dotted with acc
-    const double* Li = dinv + (long)i * NB * NB;
     double tv[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) tv[q] = acc_s[lane + 32 * q];
@@ -301,13 +360,10 @@ __global__ void __launch_bounds__(256) trsv_flow_kernel(const double* __restrict
       const int rcol = warp * 16 + rr;
       double t = 0.0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) t = fma(Li[lane + 32 * q + rcol * NB], tv[q], t);
+      for (int q = 0; q < 4; ++q) t = fma(Ls[lane + 32 * q + rcol * NB], tv[q], t);
       t = warp_sum(t);
-      if (lane == 0) x[(long)i * NB + rcol] = t;
+      if (lane == 0) flow_publish(x + (long)i * NB + rcol, t);
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_gpu(fbwd + i, 1);
   }
 }
 
@@ -327,16 +383,19 @@ inline int potrs_vec(gprc_ctx* ctx, const double* L, long n, long ld, const doub
   int nt = (int)(n / NB);
   const bool use_coop = ctx->opt_trsv == 0;
   if (!use_coop) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_flow_kernel, 256, 0) != cudaSuccess || per_sm < 1)
-      per_sm = 1;
-    const int grid = std::min(nt, ctx->sm_count * std::min(per_sm, 2));
-    int* flags = reinterpret_cast<int*>(work);
-    int* error = flags + 2 * nt;
-    GPRC_CUDA(cudaMemsetAsync(work, 0, sizeof(int) * (2 * (size_t)nt + 2), ctx->stream));
-    void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&rhs, (void*)&tmp, (void*)&x, (void*)&flags,
-                    (void*)&error};
-    GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_flow_kernel, dim3(grid), dim3(256), args, 0, ctx->stream));
+    static bool configured[64] = {false};
+    if (!configured[ctx->device & 63]) {
+      GPRC_CUDA(cudaFuncSetAttribute(trsv_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_FLOW_SMEM));
+      configured[ctx->device & 63] = true;
+    }
+    const int grid = std::min(nt, ctx->sm_count);  // one resident CTA per SM (128 KB of shared memory each)
+    int* error = reinterpret_cast<int*>(work);
+    GPRC_CUDA(cudaMemsetAsync(work, 0, sizeof(int) * 2, ctx->stream));
+    GPRC_CUDA(cudaMemsetAsync(tmp, 0xFF, sizeof(double) * n, ctx->stream));  // sentinel: "not yet computed"
+    GPRC_CUDA(cudaMemsetAsync(x, 0xFF, sizeof(double) * n, ctx->stream));
+    void* args[] = {(void*)&L, (void*)&ld, (void*)&dinv, (void*)&nt, (void*)&rhs, (void*)&tmp, (void*)&x, (void*)&error};
+    GPRC_CUDA(cudaLaunchCooperativeKernel((const void*)trsv_flow_kernel, dim3(grid), dim3(256), args, TRSV_FLOW_SMEM,
+                                          ctx->stream));
     ctx->launches++;
     return 0;
   }
