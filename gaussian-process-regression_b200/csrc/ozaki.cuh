@@ -901,26 +901,54 @@ __global__ void __launch_bounds__(THREADS, 1) update_stack_kernel(const UpdatePa
             if (CL == 1) mbar_arrive(smem_u32(empty + s));
             else tc_commit_multicast(smem_u32(empty + s), ALL);
           } else {
+            if ((p.dbg & 64) && !first) {  // experiment: the wait for this stage at the top instead of mid-step
+              mbar_wait_guarded(smem_u32(full + s), (kt / C::STAGES) & 1, p.error, 64);
+              tc_fence_after();
+            }
             const uint32_t a0 = smem_u32(smem_raw + s * C::STAGE_BYTES);
             const uint64_t ad0 = smem_desc(a0, 128, 256), bd0 = smem_desc(a0 + S * A_TILE, 128, 256);
-            int issued = 0;
+            const bool midwait = !(p.dbg & 64) && kt + 1 < kt_end;
+            // one MMA: plane a of L against planes b0 .. b0 + nb - 1 of V into the accumulators of orders a + b0 ...
+            auto piece = [&](int a, int b0, int nb, uint32_t acc) {
+              mma_i8(tmem_base + (uint32_t)((a + b0) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
+                     bd0 + (uint64_t)(b0 * (B_TILE >> 4)), instr_desc_i8(BM, BN * nb), acc);
+            };
+            auto wait_next = [&]() {
+              // the wait for the NEXT stage sits in the middle of this stage's MMAs: the tensor pipe has queued work
+              // while the issuing lane pays the try_wait / fence latency
+              mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
+              tc_fence_after();
+            };
+            if (first || !(p.dbg & 16)) {
+              // plane 0 first: accumulator a + b is first written in this chunk by plane a = 0 at the chunk's first k-step
+              int issued = 0;
 #pragma unroll
-            for (int a = 0; a < S; ++a) {
-              const int n1 = stack_first(S, a), n2 = (S - a) - n1;
+              for (int a = 0; a < S; ++a) {
+                const int n1 = stack_first(S, a), n2 = (S - a) - n1;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int b0 = h ? n1 : 0, nb = h ? n2 : n1;
-                if (nb == 0) continue;
-                if (issued == WAITPOS && kt + 1 < kt_end) {
-                  // the wait for the NEXT stage sits in the middle of this stage's MMAs: the tensor pipe has queued
-                  // work while the issuing lane pays the try_wait / fence latency
-                  mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
-                  tc_fence_after();
+                for (int h = 0; h < 2; ++h) {
+                  const int b0 = h ? n1 : 0, nb = h ? n2 : n1;
+                  if (nb == 0) continue;
+                  if (issued == WAITPOS && midwait) wait_next();
+                  piece(a, b0, nb, (!first || a > 0) ? 1u : 0u);
+                  ++issued;
                 }
-                // accumulator a + b is first written in this chunk by plane a = 0 at the chunk's first k-step
-                mma_i8(tmem_base + (uint32_t)((a + b0) * BN), ad0 + (uint64_t)(a * (A_TILE >> 4)),
-                       bd0 + (uint64_t)(b0 * (B_TILE >> 4)), instr_desc_i8(BM, BN * nb), (!first || a > 0) ? 1u : 0u);
-                ++issued;
+              }
+            } else {
+              // experiment (dbg & 16): the same MMAs with the small ones first and the widest last, so that the tensor
+              // pipe holds the most queued work while the issuing lane crosses the k-step boundary
+              int issued = 0;
+#pragma unroll
+              for (int a = S - 1; a >= 0; --a) {
+                const int n1 = stack_first(S, a), n2 = (S - a) - n1;
+#pragma unroll
+                for (int h = 1; h >= 0; --h) {
+                  const int b0 = h ? n1 : 0, nb = h ? n2 : n1;
+                  if (nb == 0) continue;
+                  if (issued == NMMA - 1 - WAITPOS && midwait) wait_next();
+                  piece(a, b0, nb, 1u);
+                  ++issued;
+                }
               }
             }
             if (CL == 1) tc_commit(smem_u32(empty + s));
