@@ -772,9 +772,9 @@ __global__ void __launch_bounds__(THREADS, 1) update128_kernel(const UpdateParam
 // is a plain 128 x (64 nb) x 32 MMA: same D / B base addresses as the single products, N = 64 nb in the instruction
 // descriptor.  With both operands in shared memory a 128 x N x 32 INT8 MMA takes max(N / 2, 32 + N / 4) clk
 // (tools/oz_test rate): the 4 KB A tile is fetched once per MMA through the 128 B/clk operand port, which is what held
-// the 28 single products (N = 64: 48 clk against a 32 clk math floor) at 54 % of the pipe.  Stacked, S = 7 needs 11
+// the 28 single products (N = 64: 48 clk against a 32 clk math floor) at 54 % of the pipe.  Stacked, S = 7 needs 10
 // MMAs per k-step (N = 256 / 192 / 128 / 64) and 912 clk instead of 1344, 98 % of the 896 clk math floor; the A tiles
-// cross the operand port 11 instead of 28 times.  Results are bit-identical to update_kernel (same integer sums).
+// cross the operand port 10 instead of 28 times.  Results are bit-identical to update_kernel (same integer sums).
 //
 // CL = 2: a cluster of two CTAs works on the SAME 64-point tile of V for two consecutive block rows of L
 // (rows 2 j and 2 j + 1 against k < 256 j).  Each CTA's producer fetches its own L digits and HALF of the V digits of
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_stack_kernel(const UpdatePa
               mbar_wait_guarded(smem_u32(full + (kt + 1) % C::STAGES), ((kt + 1) / C::STAGES) & 1, p.error, 64);
               tc_fence_after();
             };
-            if (first || !(p.dbg & 16)) {
+            if (first || (p.dbg & 16)) {
               // plane 0 first: accumulator a + b is first written in this chunk by plane a = 0 at the chunk's first k-step
               int issued = 0;
 #pragma unroll
@@ -935,8 +935,9 @@ __global__ void __launch_bounds__(THREADS, 1) update_stack_kernel(const UpdatePa
                 }
               }
             } else {
-              // experiment (dbg & 16): the same MMAs with the small ones first and the widest last, so that the tensor
-              // pipe holds the most queued work while the issuing lane crosses the k-step boundary
+              // every other k-step: the same MMAs with the small ones first and the widest last, so that the tensor pipe
+              // holds the most queued work while the issuing lane crosses the k-step boundary (commit, next descriptors):
+              // 994 instead of 1087 clk per k-step (tools/oz_test ... dbg 16 restores plane-0-first everywhere)
               int issued = 0;
 #pragma unroll
               for (int a = S - 1; a >= 0; --a) {

@@ -191,12 +191,15 @@ __device__ __forceinline__ void flow_wait(const int* flag, int* error) {
 constexpr unsigned long long TRSV_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
 constexpr int TRSV_FLOW_SMEM = NB * NB * 8 + 2 * NB * 8;  // inverted diagonal block + two 128-vectors
 
-__device__ __forceinline__ double flow_poll(const double* p, int* error) {
+// polite = true: this consumer is far from the block that is being computed right now (it cannot use the value for a
+// while), so it sleeps between polls and leaves the L2 lines of the front to the CTA on the critical path
+__device__ __forceinline__ double flow_poll(const double* p, int* error, bool polite = false) {
   unsigned long long v;
   long spin = 0;
   for (;;) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     if (v != TRSV_SENTINEL) break;
+    if (polite) __nanosleep(400);
     if (++spin > (1L << 26)) {  // seconds: a dependency that never arrives
       atomicOr(error, 1);
       __threadfence_system();
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
         for (int e = tid; e < NB * NB / 2; e += 256)
           reinterpret_cast<double2*>(Ls)[e] = __ldg(reinterpret_cast<const double2*>(Li) + e);
       }
+      const double bi = b[(long)i * NB + r];                             // off the critical path
       const double* Lrow = L + (long)i * NB + r + (long)(h * 32) * ld;  // unit u adds 64 u columns
       const double* zq = z + h * 32 + lane;                              // unit u adds 64 u
       double A[32], B[32];
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
           for (int c = 0; c < 32; ++c) B[c] = p[(long)c * ld];
         }
         {
-          const double zl = flow_poll(zq + (long)u * 64, error);
+          const double zl = flow_poll(zq + (long)u * 64, error, u + 4 < units);
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             a0 = fma(A[c], __shfl_sync(0xffffffffu, zl, c), a0);
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
           for (int c = 0; c < 32; ++c) A[c] = p[(long)c * ld];
         }
         {
-          const double zl = flow_poll(zq + (long)(u + 1) * 64, error);
+          const double zl = flow_poll(zq + (long)(u + 1) * 64, error, u + 5 < units);
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             a0 = fma(B[c], __shfl_sync(0xffffffffu, zl, c), a0);
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
       const double mine = a0 + a1;
       if (h == 1) part[r] = mine;
       __syncthreads();  // also: Ls is complete
-      if (h == 0) acc_s[r] = b[(long)i * NB + r] - (mine + part[r]);
+      if (h == 0) acc_s[r] = bi - (mine + part[r]);
       __syncthreads();
       // z_i = Linv_i acc   (explicit zeros above the diagonal of Linv_i)
       double s0 = 0.0, s1 = 0.0;
@@ -303,6 +307,8 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
       for (int e = tid; e < NB * NB / 2; e += 256)
         reinterpret_cast<double2*>(Ls)[e] = __ldg(reinterpret_cast<const double2*>(Li) + e);
     }
+    // z_i (this block's forward result, complete long ago): lane cc of warp w fetches entry 16 w + cc now
+    const double zi = (lane < 16) ? flow_poll(z + (long)i * NB + warp * 16 + lane, error) : 0.0;
     const double* Lcol = L + lane + ((long)i * NB + warp * 16) * ld;  // unit: rows 64 v .. 64 v + 63, v descending
     double A[32], B[32], acc[16];
 #pragma unroll
@@ -326,7 +332,8 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
         }
       }
       {
-        const double x0 = flow_poll(x + (long)v * 64 + lane, error), x1 = flow_poll(x + (long)v * 64 + lane + 32, error);
+        const bool far = v - 4 > vlo;
+        const double x0 = flow_poll(x + (long)v * 64 + lane, error, far), x1 = flow_poll(x + (long)v * 64 + lane + 32, error, far);
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) acc[cc] = fma(A[2 * cc + 1], x1, fma(A[2 * cc], x0, acc[cc]));
       }
@@ -339,8 +346,9 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
         }
       }
       {
-        const double x0 = flow_poll(x + (long)(v - 1) * 64 + lane, error),
-                     x1 = flow_poll(x + (long)(v - 1) * 64 + lane + 32, error);
+        const bool far = v - 5 > vlo;
+        const double x0 = flow_poll(x + (long)(v - 1) * 64 + lane, error, far),
+                     x1 = flow_poll(x + (long)(v - 1) * 64 + lane + 32, error, far);
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) acc[cc] = fma(B[2 * cc + 1], x1, fma(B[2 * cc], x0, acc[cc]));
       }
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) trsv_flow_kernel(const double* __restr
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
       const double t = warp_sum(acc[cc]);
-      if (lane == cc) acc_s[warp * 16 + cc] = flow_poll(z + (long)i * NB + warp * 16 + cc, error) - t;  // z_i: forward result
+      if (lane == cc) acc_s[warp * 16 + cc] = zi - t;
     }
     __syncthreads();  // acc_s and Ls complete
     // x_i = Linv_i^T acc: entry r is column r of Linv_i dotted with acc

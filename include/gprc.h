@@ -65,8 +65,9 @@ enum {
                             (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
   GPRC_OPT_INT8_TEST_SHRINK = 6, /* tests only: lower the per-test-point exponents of path 4 by this many bits so that
                             v leaves its fixed-point range: the overflow flag must fire and the chunk be redone in FP64 */
-  GPRC_OPT_TRSV = 7, /* alpha = L^-T L^-1 y (R/GPRclass.R:152): 0 two cooperative sweeps, grid-wide barrier per block step;
-                        1 both sweeps as one dataflow kernel (a CTA per row block, release / acquire flags) */
+  GPRC_OPT_TRSV = 7, /* alpha = L^-T L^-1 y (R/GPRclass.R:152): 1 (default) both sweeps as one dataflow kernel (a CTA per
+                        row block; consumers poll the published entries); 0 two cooperative sweeps with a grid-wide
+                        barrier per block step (round 1) */
   GPRC_OPT_INT8_TILE = 5 /* kernel of path 4 (all give the same digits; 1 and 64 are bit-identical):
                             2 (default) stacked digit planes on clusters of two CTAs: one tcgen05.mma multiplies a digit
                               plane of L with up to four planes of V (N up to 256), two block rows of L share every V digit
