@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const CovParams p) {
             for (int qb = 0; qb < 4; ++qb) {
               // separate rounding of the square and of the running sum (no FMA contraction), the order of R's
               // (x - y)^2 then colSums.  Not bit-for-bit R for D > 1: colSums accumulates in long double (80 bit on x86)
-              // and rounds once at the end, so r^2 can differ from R's by 1 ulp; the oracle sums in double like this
+              // and rounds once at the end, so r^2 can differ from R's by 1 ulp; the CPU restatement under tests/ sums in double like this
               const double df = a[qa] - b[qb];
               acc[qa][qb] = __dadd_rn(acc[qa][qb], __dmul_rn(df, df));
             }
