@@ -312,6 +312,7 @@ extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
   GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
   GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
+  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_sched), 4096));
   GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
   GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_info), sizeof(long)));
   *out = c;
@@ -334,6 +335,7 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
   c->pool_live.clear();
   cudaFree(c->d_info);
   cudaFree(c->d_scalars);
+  cudaFree(c->d_sched);
   cudaFreeHost(c->h_scalars);
   cudaFreeHost(c->h_info);
   cudaStreamSynchronize(c->stream_hi);
@@ -364,6 +366,11 @@ extern "C" int gprc_ctx_set_option(gprc_ctx* c, int option, int value) {
   if (option == GPRC_OPT_INT8_TILE) {
     GPRC_ARG(value == 1 || value == 2 || value == 64 || value == 128);
     c->opt_int8_tile = value;
+    return 0;
+  }
+  if (option == GPRC_OPT_CHOL_TILES) {
+    GPRC_ARG(value >= 0 && value <= 1000);  // progress[] lives in the 4 KB scheduler scratch: 4 + nt ints
+    c->opt_chol_tiles = value;
     return 0;
   }
   if (option == GPRC_OPT_TRSV) {

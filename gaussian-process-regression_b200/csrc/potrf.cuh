@@ -34,10 +34,17 @@ constexpr int PNB = NB / PB;     // 16
 //   (c) one thread per row solves its 8 entries of the panel against the pivot block.
 // The inverse is then formed in place: 8 x 8 diagonal blocks by substitution, and W21 = -W22 (L21 W11) level by level
 // (block sizes 8, 16, 32, 64) again with DMMAs; the product T = L21 W11 is parked in the mirrored upper block.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int j, double* linv, long* info,
-                                                         double* diag_out /* nullable: L_ii for this block */) {
-  extern __shared__ __align__(16) unsigned char pd_raw[];
-  double* S = reinterpret_cast<double*>(pd_raw);  // S[c * PD_LDS + r]
+// The body is shared by the stand-alone kernel (256 threads, __syncthreads) and the persistent tile Cholesky below, where
+// the 256 DMMA threads of a 288-thread CTA run it (NAMED: barrier 1 among those 256 threads only).
+template <bool NAMED>
+__device__ __forceinline__ void pd_sync() {
+  if (NAMED) consumer_sync();
+  else __syncthreads();
+}
+#define __syncthreads_pd() pd_sync<NAMED>()
+template <bool NAMED>
+__device__ __forceinline__ void potrf_diag_body(double* S /* shared: PD_SMEM_BYTES */, double* A, long ld, int j,
+                                                double* linv, long* info, double* diag_out) {
   double* rdiag = S + NB * PD_LDS;                // 1 / L_ii
   double* Ajj = A + (long)j * NB * (ld + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -46,7 +53,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
     const int r = e & (NB - 1), c = e >> 7;
     S[c * PD_LDS + r] = (r >= c) ? Ajj[r + (long)c * ld] : 0.0;
   }
-  __syncthreads();
+  __syncthreads_pd();
 
   for (int jb = 0; jb < PNB; ++jb) {
     const int c0 = jb * PB;
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
         cp[0] -= e0 + o0;
         cp[PD_LDS] -= e1 + o1;
       }
-      __syncthreads();
+      __syncthreads_pd();
     }
     if (warp == 0) {
       // (b) 8 x 8 pivot block: lane (row = lane & 7) holds its row; lanes 8..31 mirror lanes 0..7
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
         for (int q = 0; q < PB; ++q) S[(c0 + q) * PD_LDS + c0 + row] = (q <= row) ? a[q] : 0.0;
       }
     }
-    __syncthreads();
+    __syncthreads_pd();
     // (c) rows below the pivot block: x Ld^T = a  (forward substitution along the row's 8 entries)
     if (tid < NB && tid >= c0 + PB) {
       double x[PB];
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
 #pragma unroll
       for (int q = 0; q < PB; ++q) S[(c0 + q) * PD_LDS + tid] = x[q];
     }
-    __syncthreads();
+    __syncthreads_pd();
   }
   // write L back (explicit zeros above the diagonal: the strictly upper part was loaded as zero and never touched)
   for (int e = tid; e < NB * NB; e += 256) {
@@ -134,12 +141,12 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
       wcol[i] = (i >= ic) ? acc * rdiag[ib * PB + i] : 0.0;
     }
   }
-  __syncthreads();
+  __syncthreads_pd();
   if (tid < NB) {
 #pragma unroll
     for (int i = 0; i < PB; ++i) S[(ib * PB + ic) * PD_LDS + ib * PB + i] = wcol[i];
   }
-  __syncthreads();
+  __syncthreads_pd();
   // (e) levels: left part [gl, gl + s), right part [gr, gr + s) in units of 8
   for (int s = 1; s < PNB; s *= 2) {
     const int tiles = (PNB / (2 * s)) * s * s;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
       cp[0] = e0 + o0;
       cp[1] = e1 + o1;
     }
-    __syncthreads();
+    __syncthreads_pd();
     // phase 2: W21 = -W22 T, overwriting L21
     for (int q = warp; q < tiles; q += 8) {
       const int g = q / (s * s), rem = q - g * s * s, ti = rem / s, tj = rem - ti * s;
@@ -176,11 +183,204 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int
       cp[0] = -(e0 + o0);
       cp[PD_LDS] = -(e1 + o1);
     }
-    __syncthreads();
+    __syncthreads_pd();
   }
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e & (NB - 1), c = e >> 7;
     linv[e] = (r >= c) ? S[c * PD_LDS + r] : 0.0;  // the upper part holds scratch of the level products
+  }
+}
+#undef __syncthreads_pd
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* A, long ld, int j, double* linv, long* info,
+                                                         double* diag_out /* nullable: L_ii for this block */) {
+  extern __shared__ __align__(16) unsigned char pd_raw[];
+  potrf_diag_body<false>(reinterpret_cast<double*>(pd_raw), A, ld, j, linv, info, diag_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Round 2: the whole factorisation as ONE persistent kernel for small and medium n (n <= 16 384 by default).
+//
+// The launch sequence below (potrf_blocked) spends three dependent launches per 128-column block -- left update,
+// potrf_diag, panel solve -- and below n ~ 16k that chain, not the DMMA pipe, sets the time (n = 2048: 2.1 ms for
+// 2.9 GFLOP).  Here the factor is computed tile by tile, left-looking: task (i, j), i >= j, produces tile L_ij in one go,
+//     C   = A_ij - sum_{k<j} L_ik L_jk^T        DMMA GEMM with K = 128 j (SyrkPolicy's epilogue)
+//     i > j:  L_ij = C Linv_j^T                  DMMA GEMM with K = 128  (TrsmPolicy's epilogue)
+//     i = j:  L_jj = chol(C), Linv_j             potrf_diag_body in the shared memory of the (idle) operand ring
+// Tasks are handed out column by column by an atomic counter to a resident grid; a per-ROW progress counter
+// (progress[i] = number of finished tiles of row i, release / acquire) is the only synchronisation: task (i, j) needs
+// rows i and j up to column j, and Linv_j.  The producer lane waits per 128-wide k-block, so the GEMM of a tile streams
+// in as its operands complete, and the only thing on the critical path of column j + 1 is: diagonal block j -> panel
+// solve of tile (j+1, j) -> the last k-block of the diagonal tile (j+1, j+1).  Every prerequisite of a task has a
+// smaller task index and tasks are only handed to running CTAs, so no co-residency guarantee is needed.
+// ---------------------------------------------------------------------------------------------------------------
+struct CholPersistParams {
+  double* A;
+  long ld;
+  int nt;
+  double* dinv;
+  long* info;
+  double* diag;              // nullable
+  unsigned long long* next;  // task counter (zeroed by the host)
+  int* progress;             // [nt] finished tiles per row (zeroed by the host)
+  int* error;                // watchdog
+};
+
+__device__ __forceinline__ bool chol_wait_progress(const int* prog, int want, int* error) {
+  long long spins = 0;
+  while (ld_acquire_gpu(prog) < want) {
+    if (++spins > (1LL << 26) || *reinterpret_cast<volatile int*>(error)) {  // fail loudly instead of hanging the device
+      atomicExch(error, 1);
+      return false;
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) chol_persistent_kernel(const CholPersistParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_DOUBLES * 8);
+  uint64_t* empty = full + STAGES;
+  static_assert(PD_SMEM_BYTES <= STAGES * STAGE_DOUBLES * 8, "potrf_diag_body works inside the operand ring");
+  __shared__ long long s_item;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), GEMM_CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long total = (long long)p.nt * (p.nt + 1) / 2;
+  long long base = 0;  // k-slices pushed through the ring so far (identical for producer and consumers)
+  const WarpCoord wc;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      long long item = (long long)atomicAdd(p.next, 1ULL);
+      if (*reinterpret_cast<volatile int*>(p.error)) item = total;
+      s_item = item;
+    }
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= total) break;
+    // column-major enumeration of the lower triangle: column j holds nt - j tasks
+    int j = 0;
+    long long rest = item;
+    while (rest >= p.nt - j) {
+      rest -= p.nt - j;
+      ++j;
+    }
+    const int i = j + (int)rest;
+    double* Ctile = p.A + (long)i * NB + (long)j * NB * p.ld;
+    // ---- phase 0: C -= sum_{k<j} L_ik L_jk^T, streamed in as the tiles of rows i and j complete ----
+    {
+      TileWork w;
+      w.A = p.A + (long)i * NB;
+      w.lda = p.ld;
+      w.B = p.A + (long)j * NB;
+      w.ldb = p.ld;
+      w.k_begin = 0;
+      w.k_end = j * NB;
+      const int KT = j * (NB / BK);
+      if (warp == GEMM_CONSUMERS / 32) {
+        if (lane == 0) {
+          bool ok = true;
+          for (int kt = 0; kt < KT && ok; ++kt) {
+            if (kt % (NB / BK) == 0) {  // a new k-block: tiles (i, kb) and (j, kb) must be final
+              const int kb = kt / (NB / BK);
+              ok = chol_wait_progress(p.progress + i, kb + 1, p.error) && chol_wait_progress(p.progress + j, kb + 1, p.error);
+              fence_proxy_async();  // they were written with ordinary stores and are read by the TMA engine
+            }
+            const long long gk = base + kt;
+            const int s = (int)(gk % STAGES);
+            if (gk >= STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)(((gk / STAGES) - 1) & 1));
+            if (ok) produce_stage<false>(w, kt * BK, smem + s * STAGE_DOUBLES, smem_u32(full + s));
+            else mbar_arrive(smem_u32(full + s));  // watchdog fired: release the consumers (results are garbage, error set)
+          }
+        }
+      } else if (KT > 0) {
+        Acc acc;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          int line = threadIdx.x + qq * GEMM_CONSUMERS;
+          prefetch_l2(Ctile + (long)(line >> 3) * p.ld + (line & 7) * 16);
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+          const long long gk = base + kt;
+          const int s = (int)(gk % STAGES);
+          mbar_wait(smem_u32(full + s), (uint32_t)((gk / STAGES) & 1));
+          compute_stage<false>(smem + s * STAGE_DOUBLES, wc, acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(empty + s));
+        }
+        SyrkPolicy pol{p.A, p.ld, 0, 0, 0, 0};
+        SyrkPolicy::Tile tile{Ctile};
+        pol.epilogue(tile, acc, smem);
+        __threadfence();
+        fence_proxy_async();  // phase 1 reads this tile through the TMA engine
+      }
+      __syncthreads();
+      base += KT;
+    }
+    // ---- phase 1 ----
+    if (i == j) {
+      // diagonal tile: factor and invert in shared memory (the operand ring is idle: every stage has been consumed)
+      if (warp < GEMM_CONSUMERS / 32)
+        potrf_diag_body<true>(smem, p.A, p.ld, j, p.dinv + (long)j * NB * NB, p.info, p.diag);
+      __threadfence();
+      fence_proxy_async();  // the ring was written with ordinary stores and will be written by the TMA engine again
+      __syncthreads();
+    } else {
+      TileWork w;
+      w.A = Ctile;
+      w.lda = p.ld;
+      w.B = p.dinv + (long)j * NB * NB;  // element (k, n) of the B operand is Linv_j[n, k]
+      w.ldb = NB;
+      w.k_begin = 0;
+      w.k_end = NB;
+      constexpr int KT = NB / BK;
+      if (warp == GEMM_CONSUMERS / 32) {
+        if (lane == 0) {
+          const bool ok = chol_wait_progress(p.progress + j, j + 1, p.error);  // L_jj factored, Linv_j written
+          fence_proxy_async();  // Linv_j (another CTA) and C (this CTA, phase 0) were written with ordinary stores
+          for (int kt = 0; kt < KT; ++kt) {
+            const long long gk = base + kt;
+            const int s = (int)(gk % STAGES);
+            if (gk >= STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)(((gk / STAGES) - 1) & 1));
+            if (ok) produce_stage<false>(w, kt * BK, smem + s * STAGE_DOUBLES, smem_u32(full + s));
+            else mbar_arrive(smem_u32(full + s));
+          }
+        }
+      } else {
+        Acc acc;
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+        for (int kt = 0; kt < KT; ++kt) {
+          const long long gk = base + kt;
+          const int s = (int)(gk % STAGES);
+          mbar_wait(smem_u32(full + s), (uint32_t)((gk / STAGES) & 1));
+          compute_stage<false>(smem + s * STAGE_DOUBLES, wc, acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(empty + s));
+        }
+        TrsmPolicy pol{p.A, p.ld, nullptr, j};
+        TrsmPolicy::Tile tile{Ctile};
+        pol.epilogue(tile, acc, smem);
+        __threadfence();
+      }
+      __syncthreads();
+      base += KT;
+    }
+    if (threadIdx.x == 0) st_release_gpu(p.progress + i, j + 1);
   }
 }
 
@@ -199,6 +399,31 @@ inline int potrf_blocked(gprc_ctx* ctx, double* A, long n, long ld, double* dinv
     configured[ctx->device & 63] = true;
   }
   const int nt = (int)(n / NB);
+  if (nt >= 2 && nt <= ctx->opt_chol_tiles && ctx->d_sched) {
+    // small / medium n: one persistent kernel, tile tasks with per-row progress counters (chol_persistent_kernel)
+    static bool configured2[64] = {false};
+    if (!configured2[ctx->device & 63]) {
+      GPRC_CUDA(cudaFuncSetAttribute(chol_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+      configured2[ctx->device & 63] = true;
+    }
+    GPRC_CUDA(cudaMemsetAsync(ctx->d_sched, 0, 4096, ctx->stream));
+    CholPersistParams q;
+    q.A = A;
+    q.ld = ld;
+    q.nt = nt;
+    q.dinv = dinv;
+    q.info = d_info;
+    q.diag = ddiag;
+    q.next = reinterpret_cast<unsigned long long*>(ctx->d_sched);
+    q.error = ctx->d_sched + 2;
+    q.progress = ctx->d_sched + 4;
+    const long tasks = (long)nt * (nt + 1) / 2;
+    const int grid = (int)std::min<long>(tasks, ctx->sm_count);
+    chol_persistent_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(q);
+    ctx->launches++;
+    GPRC_CUDA(cudaGetLastError());
+    return 0;
+  }
   // outer panel width: 512 columns; 1024 once the trailing update dominates (n >= 25 600), which halves the share of
   // the tile epilogues (C read-modify-write) in the trailing SYRK: 32.0 -> 33.4 TFLOP/s at n = 50k, but slower below
   const int OB = (nt >= 200) ? 2 * OUTER_BLOCKS : OUTER_BLOCKS;

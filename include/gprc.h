@@ -65,6 +65,9 @@ enum {
                             (>= 18 944 test points, no inverse at hand) if n >= 4096; 0: FP64 paths only */
   GPRC_OPT_INT8_TEST_SHRINK = 6, /* tests only: lower the per-test-point exponents of path 4 by this many bits so that
                             v leaves its fixed-point range: the overflow flag must fire and the chunk be redone in FP64 */
+  GPRC_OPT_CHOL_TILES = 8, /* Cholesky (R/GPRclass.R:142): matrices of at most this many 128-blocks (n <= 128 * value) are
+                        factored by ONE persistent kernel (tile tasks, per-row progress counters) instead of three
+                        dependent launches per block column; 0 = never */
   GPRC_OPT_TRSV = 7, /* alpha = L^-T L^-1 y (R/GPRclass.R:152): 1 (default) both sweeps as one dataflow kernel (a CTA per
                         row block; consumers poll the published entries); 0 two cooperative sweeps with a grid-wide
                         barrier per block step (round 1) */
