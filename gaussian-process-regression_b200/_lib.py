@@ -29,7 +29,7 @@ INT8_TILE_DEFAULT = 2  # kernel variant of the INT8 pass the library starts with
 OPT_INT8_TEST_SHRINK = 6
 OPT_TRSV = 7
 OPT_CHOL_TILES = 8
-CHOL_TILES_DEFAULT = 0  # csrc/common.cuh: opt_chol_tiles
+CHOL_TILES_DEFAULT = 128  # csrc/common.cuh: opt_chol_tiles
 TRSV_DEFAULT = 1  # csrc/common.cuh: opt_trsv
 T_NAMES = ["build_k", "chol", "solve", "trtri", "build_ks", "var", "newton", "predict"]
 

@@ -67,7 +67,7 @@ struct gprc_ctx {
   int opt_int8_auto = 1;
   int opt_int8_tile = 2;   // kernel of the INT8 pass: 2 stacked planes on cluster pairs, 1 stacked planes, 64 / 128 round 1
   int opt_int8_test_shrink = 0;
-  int opt_chol_tiles = 0;  // largest n / 128 factored by the persistent tile kernel (0: never); needs d_sched
+  int opt_chol_tiles = 128;  // largest n / 128 factored by the persistent tile kernel (0: never); needs d_sched
   int opt_trsv = 1;        // 1 dataflow kernel (round 2, default), 0 cooperative sweeps with grid barriers (round 1)
   int last_predict_path = 0;
   long last_predict_chunks = 0;  // chunks of test points the most recent pointwise predict was cut into

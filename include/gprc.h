@@ -67,7 +67,7 @@ enum {
                             v leaves its fixed-point range: the overflow flag must fire and the chunk be redone in FP64 */
   GPRC_OPT_CHOL_TILES = 8, /* Cholesky (R/GPRclass.R:142): matrices of at most this many 128-blocks (n <= 128 * value) are
                         factored by ONE persistent kernel (tile tasks, per-row progress counters) instead of three
-                        dependent launches per block column; 0 = never */
+                        dependent launches per block column; default 128 (n <= 16 384), 0 = never */
   GPRC_OPT_TRSV = 7, /* alpha = L^-T L^-1 y (R/GPRclass.R:152): 1 (default) both sweeps as one dataflow kernel (a CTA per
                         row block; consumers poll the published entries); 0 two cooperative sweeps with a grid-wide
                         barrier per block step (round 1) */
