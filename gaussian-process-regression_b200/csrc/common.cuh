@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -56,6 +57,7 @@ inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 }  // namespace gprc
 
 struct gprc_ctx {
+  std::recursive_mutex mutex;  // held by DeviceGuard for the duration of every entry point (gprc.cu)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_hi = nullptr;  // high priority: the latency-bound panel factorisation (Cholesky lookahead)

@@ -2,6 +2,7 @@
 // GP hot path.  No Torch, no cuBLAS/cuSOLVER, no CPU fallback: every numerical step is one of the kernels in
 // cov.cuh / gemm.cuh / potrf.cuh / trsv.cuh / gpc.cuh.
 #include <chrono>
+#include <mutex>
 #include <climits>
 #include <algorithm>
 
@@ -22,10 +23,16 @@ thread_local std::string g_last_error;
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local gprc_ctx* tl_ctx = nullptr;  // context of the API call in flight (routes dmalloc/dfree to its pool)
 
+// Every entry point that touches a context holds one of these for its duration: it selects the context's device, makes
+// the context's caching allocator the current one, and LOCKS the context -- the pool maps, the pending-timer list and
+// the pinned scratch are not otherwise synchronised, and bindings such as ctypes release the interpreter lock around
+// the call, so two host threads may well arrive with the same (default) context.  Calls on one context are serialised;
+// different contexts run concurrently.  The mutex is recursive because entry points nest (fit -> logml helpers).
 struct DeviceGuard {
   int prev = -1;
   gprc_ctx* prev_ctx = nullptr;
-  explicit DeviceGuard(gprc_ctx* c) {
+  std::unique_lock<std::recursive_mutex> lock;
+  explicit DeviceGuard(gprc_ctx* c) : lock(c->mutex) {
     cudaGetDevice(&prev);
     if (prev != c->device) cudaSetDevice(c->device);
     prev_ctx = tl_ctx;

@@ -349,3 +349,38 @@ def test_long_predict_polls_the_interrupt_callback(gprc, ctx):
     assert len(calls) == 1
     out = g.predict(Xs[:, :1000])         # the context and the model still work
     assert np.all(np.isfinite(out))
+
+
+def test_two_host_threads_share_the_default_context(gprc, oracle):
+    """ctypes releases the GIL around every library call, so two Python threads can be inside libgprc with the SAME
+    context at once; the context serialises them (per-context mutex held by every entry point).  Each thread fits and
+    predicts its own model repeatedly; every result must equal the single-threaded one bit for bit."""
+    import threading
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(2):
+        n = 300 + 150 * t
+        X = rng.uniform(-2, 2, (2, n))
+        y = np.sin(X[0]) * np.cos(X[1]) + rng.normal(0, 0.1, n)
+        Xs = rng.uniform(-2, 2, (2, 400))
+        k = gprc.cov_func(gprc.sqrexp, l=0.8 + 0.3 * t)
+        g = gprc.GPR(X, y, 0.05, k)
+        jobs.append((X, y, Xs, k, g.predict(Xs), g.logp[0, 0]))
+    errors = []
+
+    def work(job):
+        X, y, Xs, k, want, lp = job
+        try:
+            for _ in range(20):
+                g = gprc.GPR(X, y, 0.05, k)
+                if not (np.array_equal(g.predict(Xs), want) and g.logp[0, 0] == lp):
+                    errors.append("result changed under concurrency")
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
