@@ -311,23 +311,34 @@ extern "C" int gprc_ctx_create(gprc_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   int prio_lo = 0, prio_hi = 0;
-  GPRC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  GPRC_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
-  GPRC_CUDA(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, prio_hi));
-  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
-  GPRC_CUDA(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
-  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
-  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
-  GPRC_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_sched), 4096));
-  GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
-  GPRC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_info), sizeof(long)));
+  // any failure below: release what exists so far (gprc_ctx_free copes with null members) and report
+#undef GPRC_CUDA_CTX
+#define GPRC_CUDA_CTX(call)                                                                 \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      gprc_ctx_free(c);                                                                     \
+      return gprc::set_error(-2, __FILE__, __LINE__, cudaGetErrorString(e__));              \
+    }                                                                                       \
+  } while (0)
+  GPRC_CUDA_CTX(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GPRC_CUDA_CTX(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+  GPRC_CUDA_CTX(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, prio_hi));
+  GPRC_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  GPRC_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming));
+  GPRC_CUDA_CTX(cudaEventCreateWithFlags(&c->ev_rest, cudaEventDisableTiming));
+  GPRC_CUDA_CTX(cudaMalloc(reinterpret_cast<void**>(&c->d_info), sizeof(long)));
+  GPRC_CUDA_CTX(cudaMalloc(reinterpret_cast<void**>(&c->d_scalars), 64 * sizeof(double)));
+  GPRC_CUDA_CTX(cudaMalloc(reinterpret_cast<void**>(&c->d_sched), 4096));
+  GPRC_CUDA_CTX(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalars), 64 * sizeof(double)));
+  GPRC_CUDA_CTX(cudaMallocHost(reinterpret_cast<void**>(&c->h_info), sizeof(long)));
   *out = c;
   return 0;
 }
 
 extern "C" void gprc_ctx_free(gprc_ctx* c) {
   if (!c) return;
+  {  // the guard (and with it the lock on c->mutex) must be gone before the context is deleted
   DeviceGuard g(c);
   cudaStreamSynchronize(c->stream);
   for (auto& p : c->pending) {
@@ -351,6 +362,7 @@ extern "C" void gprc_ctx_free(gprc_ctx* c) {
   cudaEventDestroy(c->ev_rest);
   cudaStreamDestroy(c->stream_hi);
   cudaStreamDestroy(c->stream);
+  }
   delete c;
 }
 
