@@ -665,7 +665,7 @@ static int ensure_inverse(gprc_ctx* c, FactorState& F) {
 constexpr long WAVE_COLS = 148L * NB;  // test points of one full wave of 128-wide tiles on 148 SMs
 
 static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long m, double max_bytes = 8.0e9,
-                            double extra_bytes_per_col = 0.0) {
+                            double extra_bytes_per_col = 0.0, double free_frac = 0.5) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   // blocks parked in this context's caching pool are available too (pool_alloc gives them back to the driver and retries
@@ -676,11 +676,12 @@ static int workspace_ensure(gprc_ctx* c, PredictWorkspace& ws, long n_pad, long 
   // per test point: Ks column + partial rows
   // (+ the INT8 path's digit planes of V, allocated by its variance pass)
   const double per_col = 8.0 * ((double)n_pad + (double)n_pad / 64 + (double)n_pad / NB + 1) + extra_bytes_per_col;
-  const double budget = std::min(max_bytes, 0.5 * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
+  const double budget = std::min(max_bytes, free_frac * (double)free_b + (ws.mc ? per_col * ws.mc : 0.0));
   long cap = (long)(budget / per_col) / NB * NB;
   cap = std::max<long>(cap, NB);
   cap = std::min<long>(cap, 1L << 20);
-  if (cap >= WAVE_COLS) cap = cap / WAVE_COLS * WAVE_COLS;  // chunks made of whole waves
+  // everything in one chunk if it fits; otherwise chunks made of whole waves
+  if (want > cap && cap >= WAVE_COLS) cap = cap / WAVE_COLS * WAVE_COLS;
   want = std::min(want, cap);
   if (ws.mc >= want) return 0;
   ws.release();
@@ -1023,7 +1024,9 @@ static int predict_pointwise_dev(gprc_ctx* c, const KSpecDev& k, const double* d
     // Big chunks: the CTAs of this path are independent (no lockstep sweep to preserve), so many waves per launch
     // amortise the per-block-row launches and leave one short tail instead of one per 148-tile chunk.
     GPRC_CHECK(oz_factor_digits_any(c, F));  // before sizing the workspace: the digit planes of L take n_pad^2 S bytes
-    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 75.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad));
+    // up to 110 GB and 70 % of what is free for the chunk (K_star^T + its digit planes): 113 664 test points per chunk at
+    // n = 50 000 (24 waves of cluster pairs), and the whole 125 000-point shard of an 8-GPU run in ONE chunk
+    GPRC_CHECK(workspace_ensure(c, ws, F.n_pad, m, 110.0e9, (double)c->opt_ozaki_digits * (double)F.n_pad, 0.7));
     const bool trace_chunks = getenv("GPRC_TRACE_CHUNKS") != nullptr;  // diagnostics: host wall time per chunk on stderr
     for (long c0 = 0; c0 < m; c0 += ws.mc) {
       const long mcur = std::min(ws.mc, m - c0);
