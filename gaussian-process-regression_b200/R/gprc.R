@@ -31,12 +31,14 @@
 .gprc_spec <- function(k) attr(k, "gprc_kernel", exact = TRUE)
 
 # ---- library options (include/gprc.h, GPRC_OPT_*) ---------------------------------------------------------------------
-# gprc_options(predict_path = 0:4, ozaki_digits = 6:8, int8_auto = 0:1, int8_tile = c(2, 1, 64, 128), gram_dmma = 0:2)
+# gprc_options(predict_path = 0:4, ozaki_digits = 6:8, int8_auto = 0:1, int8_tile = c(2, 1, 64, 128), gram_dmma = 0:2,
+#              trsv = 0:1, chol_tiles = 0:1000)
 # predict_path: 0 automatic; 1 inverse + triangular GEMM; 2 / 3 FP64 blocked substitution; 4 the substitution with its
 # products on the INT8 tensor cores (the automatic choice for >= 18 944 test points and n >= 4096).
 #' @export
 gprc_options <- function(...) {
-  ids <- c(gram_dmma = 1L, predict_path = 2L, ozaki_digits = 3L, int8_auto = 4L, int8_tile = 5L)
+  ids <- c(gram_dmma = 1L, predict_path = 2L, ozaki_digits = 3L, int8_auto = 4L, int8_tile = 5L, trsv = 7L,
+           chol_tiles = 8L)
   args <- list(...)
   stopifnot(all(names(args) %in% names(ids)))
   for (nm in names(args)) .Call(C_gprc_set_option, ids[[nm]], as.integer(args[[nm]]))

@@ -88,15 +88,16 @@ def test_stacked_kernel_is_bitwise_the_single_product_kernel(gprc, ctx):
 
 @pytest.mark.parametrize("variant,digits", [(2, 7), (1, 7), (2, 8), (1, 8), (2, 6), (64, 8), (128, 8), (128, 7)])
 def test_several_drain_rounds_against_the_oracle(gprc, oracle, ctx, variant, digits):
-    """n = 16 640 (130 block rows): the int32 accumulators are drained every 16 384 k-values (8192 with 8 digits), so the
-    last block rows run 2 (3) drain rounds.  Oracle = SciPy dpotrf / dtrtrs at the same n."""
+    """n = 20 480 (160 block rows, 80 pairs): the int32 accumulators are drained every 16 384 k-values (8192 with 8
+    digits), so the last block rows / pairs run 2 (3) drain rounds (K up to 20 352).  Oracle = SciPy dpotrf / dtrtrs at
+    the same n."""
     rng = np.random.default_rng(38)
-    n, m, D = 16640, 200, 4
+    n, m, D = 20480, 200, 4
     X = rng.uniform(-1, 1, (D, n))
     y = np.sum(np.sin(2 * X), axis=0) + rng.normal(0, 0.1, n)
     Xs = rng.uniform(-1, 1, (D, m))
     g = gprc.GPR(X, y, 0.05, gprc.cov_func(gprc.rationalquadratic, l=0.7, alpha=2.0), ctx=ctx)
-    ref = _oracle_16640(oracle, X, y, Xs)
+    ref = _oracle_big(oracle, X, y, Xs)
     got = predict_int8(gprc, ctx, g, Xs, variant, digits)
     assert_var_close(got, ref, np.ones(m), tol=1e-9 if digits >= 7 else 1e-8)
     assert abs(g.logp[0, 0] - _ORACLE_CACHE["logp"]) <= 1e-8 * abs(_ORACLE_CACHE["logp"])
@@ -105,7 +106,7 @@ def test_several_drain_rounds_against_the_oracle(gprc, oracle, ctx, variant, dig
 _ORACLE_CACHE = {}
 
 
-def _oracle_16640(oracle, X, y, Xs):
+def _oracle_big(oracle, X, y, Xs):
     if "pred" not in _ORACLE_CACHE:
         ok = oracle.cov_func(oracle.rationalquadratic, l=0.7, alpha=2.0)
         o = oracle.GPR(X, y, 0.05, ok)
