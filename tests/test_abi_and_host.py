@@ -319,8 +319,8 @@ def _load_protocol_sim(mutate=None):
 
 
 def test_int8_kernel_barrier_protocols_model():
-    """tools/oz_protocol_sim.py: the producer / MMA / relay / drain roles of the three INT8 kernels (default, wide, and the
-    CTA-pair draft that has not run on hardware) replayed with the kernels' slot / phase / count arithmetic under random
+    """tools/oz_protocol_sim.py: the producer / MMA / drain roles of the INT8 kernels (single CTA, wide two-pass, and the
+    cluster-pair kernel with multicast V stages) replayed with the kernels' slot / phase / count arithmetic under random
     latencies: no deadlock, every MMA reads the k-step it expects in every CTA, no stage overwritten or ring re-partitioned
     under outstanding reads, accumulators never written during a drain."""
     assert _load_protocol_sim()["campaign"](10) == []
@@ -329,8 +329,29 @@ def test_int8_kernel_barrier_protocols_model():
 @pytest.mark.parametrize("mutation", [
     ('            if passes == 2 and r > 0:\n                yield ("wait", pass_done[c], (r - 1) & 1)', "            pass"),
     ("                if need_wait:", "                if False:"),
-    ('                if ncta == 2:\n                    yield ("wait", peer_ready', '                if False:\n                    yield ("wait", peer_ready'),
+    ("EMPTY_COUNT = 2 ", "EMPTY_COUNT = 1 "),   # cluster pairs: a slot refilled after ONE CTA's commit instead of both
 ])
 def test_protocol_model_detects_injected_bugs(mutation):
-    """The model must have teeth: dropping the pass_done wait, the empty wait or the peer relay wait is caught."""
+    """The model must have teeth: dropping the pass_done wait or the empty wait, or letting the cluster pair refill a slot
+    after only one CTA's commit, is caught."""
     assert len(_load_protocol_sim(mutation)["campaign"](3)) > 0
+
+
+def test_bench_cpu_arms_run_at_reduced_size():
+    """bench.py's CPU legs (the only places outside tests/ that may execute oracle/): the bounded sample of the GPU arm and
+    the --impl reference pass, at sizes that take seconds, checked for internal consistency (the reference pass reproduces
+    the oracle's logp on its sample; generous <= literal; scaling laws of the phases)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    from oracle import gprc_oracle as o
+    s = bench.cpu_sample(4000, 20000, 8, 1024, 256)
+    assert s["kind"] == "port" and s["cores"] >= 1 and 0 < s["value"] <= s["literal_value"]
+    assert "scaled, not run" in s["sample"]
+    r = bench.cpu_reference_full(3000, 20000, 8, 512, n_train=1536)
+    assert r["value"] > 0 and r["literal_value"] > r["value"] and "REDUCED from 3000" in r["sample"]
+    X, y, Xs = bench.make_inputs(3000, 20000, 8)
+    ref = o.GPR(X[:, :1536], y[:1536], 0.01, o.cov_func(o.sqrexp, l=1.0))
+    got = float(r["sample"].rsplit("logp of the sample ", 1)[1])
+    assert abs(got - float(ref.logp)) <= 1e-6 * abs(float(ref.logp))

@@ -1,7 +1,7 @@
 """Discrete-event model of the mbarrier / tcgen05.commit protocols of the INT8 substitution kernels (csrc/ozaki.cuh:
-update_kernel, update128_kernel; csrc/ozaki_pair.cuh: update_pair_kernel).  It replays the producer, MMA-issuer, relay
-and drain roles with the kernels' own loop structure, slot / phase arithmetic and barrier counts under random latencies
-and checks, for every schedule, that
+update_kernel, update128_kernel, and update_stack_kernel<S, 2> -- clusters of two CTAs that share every V digit stage
+through TMA multicast).  It replays the producer, MMA-issuer and drain roles with the kernels' own loop structure,
+slot / phase arithmetic and barrier counts under random latencies and checks, for every schedule, that
 
   * nothing deadlocks (every role finishes),
   * every MMA reads a stage that holds the k-step it expects, in every CTA whose shared memory it reads,
@@ -13,8 +13,10 @@ mbarrier semantics modelled: `count` pending arrivals per phase, phase parity; t
 parity P has completed; a TMA stage is one arrival (arrive.expect_tx) plus its bytes (second pending unit); tcgen05.commit
 arrives when every MMA issued before it (in order) has completed; the multicast form arrives in both CTAs.
 
-The hardware is the authority (tools/oz_test); this model exists to catch slot / phase / count mistakes before GPU time is
-spent on them -- it was written for the CTA-pair draft, which has not run on hardware yet.
+The hardware is the authority (tools/oz_test: all three kernels are bit-identical to the host digit emulation on a B200);
+this model exists to catch slot / phase / count mistakes before GPU time is spent on them, and it documents WHY the
+cluster protocol is safe: a ring slot is refilled -- by either CTA's multicast copy -- only after BOTH CTAs' MMAs have
+read it (`empty` counts two commits, each multicast to both CTAs).
 
     python tools/oz_protocol_sim.py            # a few hundred random schedules of each kernel
 """
@@ -106,7 +108,8 @@ class TensorPipe:
 
 
 def simulate(kind, KT, KT_CHUNK, stages0, stages1, seed):
-    """kind: 'narrow' (one pass per chunk), 'wide' (two passes), 'pair' (two CTAs, two passes)."""
+    """kind: 'narrow' (one pass per chunk: update_kernel, update_stack_kernel<S, 1>), 'wide' (two passes: update128_kernel).
+    ('pair' models a cta_group::2 design with a relay warp that was drafted in round 1 and never shipped.)"""
     rng = random.Random(seed)
     sim = Sim(rng)
     ncta = 2 if kind == "pair" else 1
@@ -244,16 +247,120 @@ def simulate(kind, KT, KT_CHUNK, stages0, stages1, seed):
     return errors
 
 
+def simulate_stackpair(KT, KT_CHUNK, stages, seed, empty_count=2):
+    """update_stack_kernel<S, 2>: two CTAs on the same 64-point V tile, block rows 2j and 2j + 1.
+    Per CTA: producer (own L digits + HALF of the V stage, multicast into both CTAs' shared memory at the same offset,
+    completing on both CTAs' full[s]), MMA issuer (own tensor pipe, cta_group::1; tcgen05.commit multicast onto both CTAs'
+    empty[s]), four drain warps (own tensor memory).  full[s] = 1 arrival (arrive.expect_tx) + three byte deliveries
+    (own L, V half of CTA 0, V half of CTA 1); empty[s] counts `empty_count` commits (2 in the kernel)."""
+    rng = random.Random(seed)
+    sim = Sim(rng)
+    nchunks = (KT + KT_CHUNK - 1) // KT_CHUNK
+    full = [[Barrier(4, "full%d.%d" % (c, i)) for i in range(stages)] for c in range(2)]
+    empty = [[Barrier(empty_count, "empty%d.%d" % (c, i)) for i in range(stages)] for c in range(2)]
+    tmem_full = [Barrier(1, "tmem_full%d" % c) for c in range(2)]
+    tmem_empty = [Barrier(4, "tmem_empty%d" % c) for c in range(2)]
+    content = [[dict(A=None, h0=None, h1=None) for _ in range(stages)] for _ in range(2)]
+    readers = [[0] * stages for _ in range(2)]
+    acc = [dict(draining=0, complete=-1) for _ in range(2)]
+    pipes = [TensorPipe(sim), TensorPipe(sim)]
+    errors = []
+
+    def land(c, s, part, kt):
+        def fn():
+            if readers[c][s] != 0:
+                errors.append("CTA %d: stage %d part %s overwritten with %d reads outstanding" % (c, s, part, readers[c][s]))
+            content[c][s][part] = kt
+            try:
+                full[c][s].arrive()
+            except AssertionError as e:
+                errors.append(str(e))
+        return fn
+
+    def producer(c):
+        for kt in range(KT):
+            s = kt % stages
+            if kt >= stages:
+                yield ("wait", empty[c][s], ((kt // stages) - 1) & 1)
+            yield ("delay", rng.uniform(0.05, 0.3))
+            full[c][s].arrive()                                            # arrive.expect_tx(whole stage)
+            sim.at(rng.uniform(1.0, 6.0), land(c, s, "A", kt))               # own L digits
+            for dst in range(2):                                           # this CTA's half of V, multicast to both
+                sim.at(rng.uniform(1.0, 6.0), land(dst, s, "h%d" % c, kt))
+
+    def mma(c):
+        kt = 0
+        for ch in range(nchunks):
+            if ch > 0:
+                yield ("wait", tmem_empty[c], (ch - 1) & 1)
+            kt_end = min(KT, (ch + 1) * KT_CHUNK)
+            while kt < kt_end:
+                s = kt % stages
+                yield ("wait", full[c][s], (kt // stages) & 1)
+                readers[c][s] += 1
+
+                def execute(c=c, s=s, kt=kt, ch=ch):
+                    if acc[c]["draining"]:
+                        errors.append("CTA %d: MMA of chunk %d wrote the accumulators during a drain" % (c, ch))
+                    got = content[c][s]
+                    if not (got["A"] == kt and got["h0"] == kt and got["h1"] == kt):
+                        errors.append("CTA %d: MMA kt %d read stage %d holding %s" % (c, kt, s, got))
+                    readers[c][s] -= 1
+                pipes[c].push(rng.uniform(0.3, 1.5), execute)
+
+                def commit_empty(s=s):                                     # tcgen05.commit ... multicast::cluster, mask 0b11
+                    for dst in range(2):
+                        try:
+                            empty[dst][s].arrive()
+                        except AssertionError as e:
+                            errors.append(str(e))
+                pipes[c].push(0.01, commit_empty)
+                yield ("delay", rng.uniform(0.02, 0.3))
+                kt += 1
+
+            def commit_chunk(c=c, ch=ch):
+                acc[c]["complete"] = ch
+                tmem_full[c].arrive()
+            pipes[c].push(0.01, commit_chunk)
+
+    def drain(c, w):
+        for ch in range(nchunks):
+            yield ("wait", tmem_full[c], ch & 1)
+            if acc[c]["complete"] < ch:
+                errors.append("CTA %d: drain of chunk %d started before its MMAs completed" % (c, ch))
+            acc[c]["draining"] += 1
+            yield ("delay", rng.uniform(0.5, 3.0))
+            acc[c]["draining"] -= 1
+            tmem_empty[c].arrive()
+
+    for c in range(2):
+        sim.spawn(producer(c), "producer%d" % c)
+        sim.spawn(mma(c), "mma%d" % c)
+        for w in range(4):
+            sim.spawn(drain(c, w), "drain%d.%d" % (c, w))
+    if not sim.run():
+        errors.append("deadlock: %d roles still waiting at t = %.1f" % (sim.live, sim.t))
+    return errors
+
+
+EMPTY_COUNT = 2   # commits an `empty` barrier of update_stack_kernel<S, 2> waits for (tests mutate this to 1)
+
+
 def campaign(n_seeds=40):
     """Random schedules over the shapes the kernels meet: K below / at / above the ring depth, 1 to 3 drain intervals."""
     failures = []
     shapes = [(4, 512), (5, 512), (12, 512), (40, 16), (37, 16), (96, 32), (64, 64)]   # (k-steps, k-steps per chunk)
-    for kind, st0, st1 in (("narrow", 5, 5), ("wide", 7, 3), ("pair", 8, 5)):
+    for kind, st0, st1 in (("narrow", 5, 5), ("wide", 7, 3)):
         for KT, chunk in shapes:
             for seed in range(n_seeds):
                 errs = simulate(kind, KT, chunk, st0, st1, seed * 7919 + KT)
                 if errs:
                     failures.append((kind, KT, chunk, seed, errs[:3]))
+    for KT, chunk in shapes:
+        for seed in range(n_seeds):
+            errs = simulate_stackpair(KT, chunk, 5, seed * 7919 + KT, EMPTY_COUNT)
+            if errs:
+                failures.append(("stackpair", KT, chunk, seed, errs[:3]))
     return failures
 
 
