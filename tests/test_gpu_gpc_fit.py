@@ -106,6 +106,25 @@ def test_gradient_as_coded_matches_oracle(gprc, oracle):
         ref = oracle.dens_deriv(X, y, 0.05, name, v)
         got = obj.dens_deriv(name, v)
         np.testing.assert_allclose(got, ref, rtol=1e-6)
+    # the other two derivatives of cov_dict (R/fit.R:10-13, 20-22), as coded -- including what R itself evaluates to NaN:
+    # gammaexp's deriv(x, y, gamma, l) is 0 * log(0) = NaN on the diagonal (r = 0), so its first component is NaN;
+    # polynomial's second component is (x.y + sigma)^p * log(x.y + sigma) with a negative base somewhere -> NaN.
+    # (fit() only ever uses the gammaexp gradient -- BFGS -- and the NaN is part of the trajectory it then takes.)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = oracle.dens_deriv(X, y, 0.05, "gammaexp", [0.4, 1.3])
+    got = obj.dens_deriv("gammaexp", [0.4, 1.3])
+    assert np.isnan(ref[0]) and np.isnan(got[0])
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-6)
+    Xp = np.array([[-1.5, -0.4, 0.3, 1.2], [0.5, -1.1, 0.9, -0.2]])      # 4 points: the noise-free K of degree 2 is regular
+    yp = np.array([0.3, -1.0, 0.5, 2.0])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = oracle.dens_deriv(Xp, yp, 0.05, "polynomial", [0.7, 2.0])
+    got = gprc.Objective(Xp, yp, 0.05).dens_deriv("polynomial", [0.7, 2.0])
+    assert np.isnan(ref[1]) and np.isnan(got[1])
+    np.testing.assert_allclose(got[0], ref[0], rtol=1e-6)
 
 
 def test_gradient_textbook_is_the_derivative_of_dens(gprc):
