@@ -56,6 +56,7 @@ SIGNATURES = {
     "gprc_ctx_set_interrupt": (C.c_int, [_P, C.CFUNCTYPE(C.c_int, C.c_void_p), _P]),
     "gprc_ctx_reset_timers": (None, [_P]),
     "gprc_ctx_get_timers": (C.c_int, [_P, c_double_p, c_long_p]),
+    "gprc_ctx_trim": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "gprc_ctx_last_predict_path": (C.c_int, [_P]),
     "gprc_ctx_last_predict_chunks": (C.c_long, [_P]),
     "gprc_ctx_mark": (C.c_int, [_P, C.c_int]),
@@ -201,6 +202,12 @@ class Context:
         launches = C.c_long(0)
         check(self.lib.gprc_ctx_get_timers(self.handle, ms, C.byref(launches)))
         return {n: ms[i] for i, n in enumerate(T_NAMES)}, launches.value
+
+    def trim(self):
+        """release the context's cached device blocks; returns the number of bytes handed back to the driver"""
+        n = C.c_ulonglong(0)
+        check(self.lib.gprc_ctx_trim(self.handle, C.byref(n)))
+        return int(n.value)
 
     def last_predict_path(self):
         return int(self.lib.gprc_ctx_last_predict_path(self.handle))

@@ -460,6 +460,18 @@ extern "C" int gprc_ctx_get_timers(gprc_ctx* c, double* ms, long* launches) {
   return 0;
 }
 
+// give the blocks parked in the context's caching allocator back to the driver (they are otherwise only released when an
+// allocation fails, or with the context); returns the number of bytes released through *bytes (nullable)
+extern "C" int gprc_ctx_trim(gprc_ctx* c, unsigned long long* bytes) {
+  GPRC_ARG(c != nullptr);
+  DeviceGuard g(c);
+  GPRC_CUDA(cudaStreamSynchronize(c->stream));
+  GPRC_CUDA(cudaStreamSynchronize(c->stream_hi));
+  if (bytes) *bytes = (unsigned long long)c->pool_cached_bytes;
+  pool_trim(c);
+  return 0;
+}
+
 extern "C" int gprc_ctx_last_predict_path(gprc_ctx* c) { return c ? c->last_predict_path : 0; }
 extern "C" long gprc_ctx_last_predict_chunks(gprc_ctx* c) { return c ? c->last_predict_chunks : 0; }
 

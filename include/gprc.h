@@ -126,6 +126,9 @@ int gprc_ctx_get_timers(gprc_ctx* ctx, double* ms /* GPRC_T_COUNT */, long* kern
 int gprc_ctx_mark(gprc_ctx* ctx, int slot /* 0..7 */);
 int gprc_ctx_elapsed_ms(gprc_ctx* ctx, int slot_start, int slot_stop, double* ms);
 /* variance-pass path (1..4, see GPRC_OPT_PREDICT_PATH) the most recent predict on this context resolved to; 0 = none yet */
+/* Device memory freed by the library is kept in a per-context caching allocator (an optimiser calls gprc_logml hundreds
+   of times); this hands the parked blocks back to the driver.  *bytes (nullable) = bytes released. */
+int gprc_ctx_trim(gprc_ctx* ctx, unsigned long long* bytes);
 int gprc_ctx_last_predict_path(gprc_ctx* ctx);
 /* chunks of test points that predict was cut into (each chunk reads the factor once: bench.py's algorithmic bytes) */
 long gprc_ctx_last_predict_chunks(gprc_ctx* ctx);

@@ -164,3 +164,25 @@ def test_cov_matrix_closure_goes_through_host(gprc, oracle):
     kappa = lambda x, y: np.exp(-3 * (x - y) ** 2)[0]
     X = np.arange(-1, 1.0001, 0.1).reshape(1, -1)
     np.testing.assert_array_equal(gprc.covariance_matrix(X, X, kappa), oracle.covariance_matrix(X, X, kappa))
+
+
+def test_context_trim_releases_the_cached_blocks(gprc):
+    """gprc_ctx_trim: blocks freed by the library stay in the context's pool until trimmed; afterwards the driver reports
+    them free again and the context keeps working."""
+    import torch
+    ctx = gprc.Context(0)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, (3, 3000))
+    y = rng.normal(size=3000)
+    g = gprc.GPR(X, y, 0.1, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    g.predict(X[:, :100])
+    del g
+    free0 = torch.cuda.mem_get_info(0)[0]
+    released = ctx.trim()
+    assert released >= 8 * 3072 * 3072                    # at least the factor
+    assert torch.cuda.mem_get_info(0)[0] >= free0 + released // 2
+    assert ctx.trim() == 0
+    g = gprc.GPR(X, y, 0.1, gprc.cov_func(gprc.sqrexp, l=1.0), ctx=ctx)
+    assert np.isfinite(g.logp[0, 0])
+    del g
+    ctx.close()
