@@ -24,8 +24,15 @@
 //
 // Kernel structure (one CTA per 128 L-rows x 64 test points, 192 threads):
 //   warp 0   producer: two bulk copies per k-step into a ring of shared-memory stages (full/empty mbarriers)
-//   warp 1   allocates TMEM; one lane issues S (S + 1) / 2 tcgen05.mma per k-step, tcgen05.commit releases the stage
+//   warp 1   allocates TMEM; one lane issues the MMAs of a k-step, tcgen05.commit releases the stage
 //   warps 2-5 drain TMEM (tcgen05.ld 32x32b), combine the orders, scale and update R in place.
+// Kernels in this file, newest first (all produce the same digits; GPRC_OPT_INT8_TILE selects):
+//   update_stack_kernel<S, 2>  DEFAULT.  Stacked digit planes (one MMA = plane a of L x up to four planes of V, N <= 256:
+//                              10 MMAs per k-step for S = 7 instead of 28) on clusters of two CTAs that share every V
+//                              stage through TMA multicast (two block rows of L per launch).  91.7 % of the INT8 pipe.
+//   update_stack_kernel<S, 1>  the same without clusters (one block row per launch; also the odd last block row).
+//   update_kernel<S, TS>       round 1: one MMA per digit pair (TS: the L tiles staged in tensor memory -- tools/oz_test only).
+//   update128_kernel<S>        round 1: 128 x 128 tiles, the orders in two passes.
 #pragma once
 #include "common.cuh"
 
