@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, first GPU call: stacked-plane INT8 kernels (checks against the digit emulation, rates), the whole GPU tier,
 # reduced-size bench per kernel variant
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call1
 : > $O.oz.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 10 (1 GPU): the driver's sequence -- GPU tier, smoke, bench with --steps 20 --warmup 5
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call10
 ( time timeout 1100 python -m pytest tests -x -q -m gpu > $O.pytest.log 2>&1 ) 2> $O.pytest.time; echo "pytest rc=$?"; tail -3 $O.pytest.log; tail -3 $O.pytest.time

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 11 (8 GPUs): the driver's 8-GPU invocation with the final defaults
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call11
 ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > $O.bench_8gpu.json 2> $O.bench_8gpu.err ) 2> $O.time; echo "bench8 rc=$?"; tail -3 $O.time; tail -c 300 $O.bench_8gpu.err

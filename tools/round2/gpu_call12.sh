@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 12 (1 GPU): full ncu capture of the final stacked-pair kernel (widest MMAs last)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call12
 tools/oz_test time 7 16384 18944 63 5 0 > $O.oz_plain.log 2>&1 && \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 13 (2 GPUs): BASELINE config 3 (fit() multi-start, rational quadratic, n = 5000, 16 starts) on 1 and 2 GPUs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call13
 timeout 400 python tools/bench_c3.py > $O.c3_1gpu.json 2> $O.c3_1gpu.err; echo "c3 1 GPU rc=$?"; cat $O.c3_1gpu.json | tail -1 | head -c 700; echo

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 15 (4 GPUs): the driver's invocation on 4 and on 2 of the box's GPUs with the final defaults
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call15
 for N in 4 2; do

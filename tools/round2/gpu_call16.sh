@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, last GPU call: the GPU tier, smoke, and bench.py with no flags
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call16
 ( time timeout 900 python -m pytest tests -x -q -m gpu --durations=5 > $O.pytest.log 2>&1 ) 2> $O.pytest.time; echo "pytest rc=$?"; tail -9 $O.pytest.log; tail -3 $O.pytest.time | head -1

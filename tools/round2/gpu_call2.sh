@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, second GPU call: whole GPU tier (golden at full size included), full-size C4 bench, launch list + full capture
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call2
 timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $O.pytest.log 2>&1; echo "pytest rc=$?"; tail -30 $O.pytest.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, third GPU call (1 GPU): the driver's own invocations -- reference arm, then the bench with --steps 20 --warmup 5
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call3
 nproc; free -g | head -2

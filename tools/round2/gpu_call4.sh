@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, 8-GPU call: dist tests, C4 bench on 8 GPUs, C5 (n = 200 000) factorisation with the per-panel timeline
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call4
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 5 (1 GPU): dataflow TRSV (tests + timing), launch lists of C2 (GPC) and of a 1/8 shard of the C4 step
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call5
 timeout 600 python -m pytest tests/test_gpu_trsv_flow.py -m gpu -x -q > $O.pytest_trsv.log 2>&1; echo "pytest trsv rc=$?"; tail -5 $O.pytest_trsv.log

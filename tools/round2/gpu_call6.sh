@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 6 (1 GPU): dataflow TRSV v2 (tests + timing), S = 6 bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call6
 timeout 300 python -m pytest tests/test_gpu_trsv_flow.py -m gpu -x -q > $O.pytest_trsv.log 2>&1; echo "pytest trsv rc=$?"; tail -5 $O.pytest_trsv.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 7 (1 GPU): reversed MMA order as default (bit-exact checks), TRSV v2.1 default, whole GPU tier, C4 bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call7
 for a in "check 7 1024 256 3 4 0" "check 7 2048 384 7 5 0" "check 8 16640 128 64 5 0" "check 6 1024 256 3 5 0" "check 7 16896 128 131 4 0" "time 7 16384 18944 63 5 0" "time 7 16384 18944 127 4 0"; do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 8 (1 GPU): persistent tile Cholesky (tests + timing)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call8
 timeout 600 python -m pytest tests/test_gpu_chol_persistent.py -m gpu -x -q > $O.pytest_chol.log 2>&1; echo "pytest chol rc=$?"; tail -15 $O.pytest_chol.log

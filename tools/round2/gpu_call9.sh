@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 9 (2 GPUs): dist tests with the new defaults, C4 bench on 2 GPUs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 O=gpurun_out/r2_call9
 timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q > $O.pytest_dist.log 2>&1; echo "pytest dist rc=$?"; tail -5 $O.pytest_dist.log
