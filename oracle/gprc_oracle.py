@@ -16,7 +16,7 @@ SURVEY.md section 4) are checked in tests/test_oracle.py.  Of the six model-sele
 tests/testthat/test-fit.R the first three (linear, constant, polynomial) are reproduced; the last three (sqrexp,
 gammaexp, rationalquadratic for amplitude-5 targets) are NOT attainable by any faithful implementation of R/fit.R --
 even the global maximum of the expected family's likelihood lies > 7 below the polynomial family's score, confirmed
-in 40-digit arithmetic independent of this file (tools/test_fit_R_study.py, profiles/r2_test_fit_R_study.md); the test
+in 40-digit arithmetic independent of this file (tests/probes/fit_R_study.py, profiles/r2_test_fit_R_study.md); the test
 asserts that property.  Everything else (logp, alpha, L, logq, f_hat, gradients, n > 25) is PARITY UNPINNED by the
 reference and pinned only by this restatement.
 

@@ -1,6 +1,6 @@
 """BASELINE config 3: fit() objective for the rational-quadratic kernel, n = 5000, d = 4, 16 starts, sharded across
 the ranks (torchrun) -- each rank runs the optimiser trajectories of its share of start vectors, no data-path
-collective; the (par, value) pairs are all-gathered.  python tools/bench_c3.py (1 GPU) or under torchrun."""
+collective; the (par, value) pairs are all-gathered.  python tests/probes/bench_c3.py (1 GPU) or under torchrun."""
 import json
 import os
 import sys

@@ -11,7 +11,7 @@ an independent 40-digit evaluation (mpmath: its own Cholesky, nothing shared wit
       R/GPRclass.R:394-402) and the targets have amplitude 5, a > 4-sigma event under every such prior, whereas
       (sigma + x y)^p scales freely.
 
-    python tools/test_fit_R_study.py            # prints the table of profiles/r2_test_fit_R_study.md
+    python tests/probes/fit_R_study.py            # prints the table of profiles/r2_test_fit_R_study.md
 """
 import math
 import os
@@ -19,7 +19,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import gprc_oracle as o  # noqa: E402
 

@@ -75,11 +75,10 @@ def test_fit_model_selection_test_fit_R():
     of R/fit.R, R included: the kernels have unit prior variance and the targets amplitude 5, so even the global maximum
     of the expected family's log marginal likelihood lies > 7 below the polynomial family's score -- shown here on a
     parameter grid and, independently of NumPy / LAPACK / the oracle's dens(), in 40-digit arithmetic
-    (tools/test_fit_R_study.py, profiles/r2_test_fit_R_study.md).  What is asserted is that property, not an outcome."""
+    (tests/probes/fit_R_study.py, profiles/r2_test_fit_R_study.md).  What is asserted is that property, not an outcome."""
     import importlib.util
     spec = importlib.util.spec_from_file_location(
-        "test_fit_R_study", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
-                                         "test_fit_R_study.py"))
+        "fit_R_study", os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes", "fit_R_study.py"))
     study = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(study)
     X, Ys = study.targets()
