@@ -6,7 +6,10 @@
 typedef struct SEXPREC* SEXP;
 typedef ptrdiff_t R_xlen_t;
 typedef enum { FALSE = 0, TRUE } Rboolean;
+#define LGLSXP 10
+#define INTSXP 13
 #define REALSXP 14
+#define STRSXP 16
 #define VECSXP 19
 extern SEXP R_NilValue, R_NamesSymbol;
 extern double R_NaReal;
