@@ -282,8 +282,27 @@ static int digits_selftest() {
   if (!ovf) ++bad;
   if ((long long)S * oz::Cfg<S>::KC * 16384LL >= (1LL << 31)) ++bad;  // all S pairs of one order at (-128)^2 for KC steps
   if (oz::Cfg<S>::SMEM_BYTES > 227 * 1024 || S * oz::BN > oz::TMEM_COLS) ++bad;
-  printf("digits S=%d: %ld failures (KC=%d, stages=%d, smem=%d B)\n", S, bad, oz::Cfg<S>::KC, oz::Cfg<S>::STAGES,
-         oz::Cfg<S>::SMEM_BYTES);
+  // stacked planes (update_stack_kernel): the MMAs of one k-step must cover every digit pair (a, b), a + b < S, exactly
+  // once, each with N = 64 nb <= 256 and its accumulator columns inside the S * 64 allocated ones
+  {
+    int cover[8][8] = {{0}}, count = 0;
+    for (int a = 0; a < S; ++a) {
+      const int n1 = oz::stack_first(S, a), n2 = (S - a) - n1;
+      for (int h = 0; h < 2; ++h) {
+        const int b0 = h ? n1 : 0, nb = h ? n2 : n1;
+        if (nb == 0) continue;
+        ++count;
+        if (nb < 1 || 64 * nb > 256 || (a + b0 + nb) * oz::BN > S * oz::BN) ++bad;
+        for (int b = b0; b < b0 + nb; ++b) ++cover[a][b];
+      }
+    }
+    for (int a = 0; a < 8; ++a)
+      for (int b = 0; b < 8; ++b)
+        if (cover[a][b] != ((a < S && b < S && a + b < S) ? 1 : 0)) ++bad;
+    if (count != oz::stack_mmas(S)) ++bad;
+  }
+  printf("digits S=%d: %ld failures (KC=%d, stages=%d, smem=%d B, %d stacked MMAs per k-step)\n", S, bad, oz::Cfg<S>::KC,
+         oz::Cfg<S>::STAGES, oz::Cfg<S>::SMEM_BYTES, oz::stack_mmas(S));
   return bad ? 1 : 0;
 }
 
